@@ -1,0 +1,142 @@
+/* libsmk.so -- C ABI of the B200-native SaclayMocks hot path.
+ *
+ * The reference (igmhub/SaclayMocks) is pure Python and has no FFI; its seams for this path
+ * are the in-Python calls listed next to each entry point below.
+ * Conventions:
+ *   - every function returns 0 on success or a negative SMK_ERR_* code; the message is
+ *     available from smk_last_error() (thread-local); nothing throws across the boundary;
+ *   - array arguments are caller-owned DEVICE pointers unless the name ends in _host;
+ *     the library owns only the plan/workspaces inside smk_ctx;
+ *   - one smk_ctx per GPU (per rank); calls are asynchronous on the ctx stream unless
+ *     stated otherwise;
+ *   - complex data are interleaved float pairs (numpy complex64 layout).
+ *
+ * Layout of the k-space box ("boxk"): [nx_k][ny_k][pitch] complex64 with
+ * pitch = smk_boxk_pitch() >= nz/2+1 (rows padded to a multiple of 16 complex = 128 B).
+ * Single rank: nx_k = nx, ny_k = ny.  With R ranks the real boxes are x-slabs
+ * [nx/R][ny][nz] and boxk is kept transposed as y-slabs: [nx][ny/R][pitch].
+ */
+#ifndef SMK_H
+#define SMK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMK_OK 0
+#define SMK_ERR_ARG (-1)
+#define SMK_ERR_CUDA (-2)
+#define SMK_ERR_UNSUPPORTED (-3)
+#define SMK_ERR_NULL_BOX (-4) /* all-zero or NaN output: make_boxes.py:63-70,100-105 raises ValueError */
+
+typedef struct smk_ctx smk_ctx;
+
+/* Products of make_boxes.py (bin/make_boxes.py:242-431), in the order the reference writes them. */
+enum smk_product {
+  SMK_PLN1 = 0, /* boxln_1: boxk * Pln1            make_boxes.py:247 */
+  SMK_PLN2 = 1, /* boxln_2                         make_boxes.py:265 */
+  SMK_PLN3 = 2, /* boxln_3                         make_boxes.py:274 */
+  SMK_P0 = 3,   /* box (delta): boxk * P0, kept    make_boxes.py:289-291 */
+  SMK_ETA_XX = 4, /* boxk*P0 * kx kx / k^2         make_boxes.py:324 */
+  SMK_ETA_YY = 5,
+  SMK_ETA_ZZ = 6,
+  SMK_ETA_XY = 7,
+  SMK_ETA_XZ = 8,
+  SMK_ETA_YZ = 9,
+  SMK_VX = 10, /* boxk*P0 * -i kx/k^2 * H0 * dD/dz(0)   make_boxes.py:403 */
+  SMK_VY = 11,
+  SMK_VZ = 12,
+  SMK_NPRODUCTS = 13
+};
+
+const char* smk_last_error(void);
+int smk_version(void);
+
+/* ---- context / plan.  Replaces the pyfftw plan + wisdom handling of make_boxes.py:192-203.
+ * dcell = cell size in Mpc/h (make_boxes.py -pixel).  stream = cudaStream_t (NULL = default stream).
+ * rank/nranks describe the slab decomposition; nranks > 1 requires nx % nranks == 0 and ny % nranks == 0. */
+int smk_ctx_create(smk_ctx** ctx, int nx, int ny, int nz, double dcell, int rank, int nranks, void* stream);
+int smk_ctx_destroy(smk_ctx* ctx);
+int smk_boxk_pitch(const smk_ctx* ctx);           /* complex elements per kz row */
+size_t smk_boxk_elems(const smk_ctx* ctx);        /* complex elements of this rank's boxk */
+size_t smk_box_elems(const smk_ctx* ctx);         /* float elements of this rank's real x-slab */
+size_t smk_workspace_bytes(const smk_ctx* ctx);   /* bytes the ctx holds in HBM */
+int smk_sync(smk_ctx* ctx);                       /* cudaStreamSynchronize(ctx stream) */
+
+/* ---- white noise.  Replaces the np.random.normal plane loop of DrawGRF_boxk (make_boxes.py:46-48)
+ * with Philox4x32-10 keyed by (seed, global cell index): identical for any slab decomposition. */
+int smk_noise_philox(smk_ctx* ctx, uint64_t seed, float* box_slab);
+
+/* ---- forward transform of DrawGRF_boxk (make_boxes.py:52-54): unnormalised r2c over (x,y,z).
+ * box_slab: [nx/R][ny][nz] float (preserved).  If box_slab is NULL the noise is generated inside the
+ * z-pass from (seed) and never touches HBM.  boxk: see layout above.
+ * Multi-rank: the caller performs the slab exchange between smk_fft_r2c_local (z and y passes, output in
+ * send layout) and smk_fft_r2c_finish (x pass); single rank: smk_fft_r2c does everything. */
+int smk_fft_r2c(smk_ctx* ctx, const float* box_slab, uint64_t seed, void* boxk);
+int smk_fft_r2c_local(smk_ctx* ctx, const float* box_slab, uint64_t seed, void* sendbuf);
+int smk_fft_r2c_finish(smk_ctx* ctx, const void* recvbuf, void* boxk);
+
+/* ---- one product of make_boxes.py: boxk *= W (or k-factor) followed by FFTandStore's arithmetic
+ * (make_boxes.py:77-105): unnormalised c2r, /= nx*ny*nz, sum and sum of squares for sigma = np.std(box).
+ * boxk is preserved, except that product SMK_P0 with store_p0 != 0 replaces it by boxk*P0 exactly like
+ * make_boxes.py:289-291 (the eta and velocity products must then be fed that array).
+ * wtable: float [nx_k][ny_k][nz/2+1] (unpadded rows, the HDU of P<NX>-<NY>-<NZ>.fits), required for
+ * SMK_PLN1..SMK_P0, ignored otherwise.  dgrowth0 = dD/dz(z=0) (make_boxes.py:313), used by SMK_V*.
+ * out_slab: [nx/R][ny][nz] float.  stats (device, 2 doubles, accumulated: zero them first): sum, sum of squares
+ * of this rank's slab.
+ * Multi-rank: smk_synth_c2r_local does the x pass into sendbuf; after the caller's all-to-all,
+ * smk_synth_c2r_finish does the y and z passes from recvbuf. */
+int smk_synth_c2r(smk_ctx* ctx, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
+                  float* out_slab, double* stats);
+int smk_synth_c2r_local(smk_ctx* ctx, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
+                        void* sendbuf);
+int smk_synth_c2r_finish(smk_ctx* ctx, void* recvbuf, float* out_slab, double* stats);
+
+/* Host-buffer convenience wrapper of the whole DrawGRF_boxk + 13 x FFTandStore chain (the call a
+ * make_boxes.py replacement makes): noise from `noise_host` ([nx][ny][nz] float) or Philox(seed) when NULL,
+ * weight tables from host, every requested product copied back to out_host[p] (NULL = skip that product).
+ * sigma_out[p] = std of product p.  Synchronous.  Single rank only. */
+int smk_make_boxes_host(smk_ctx* ctx, const float* noise_host, uint64_t seed, const float* const wtables_host[4],
+                        double dgrowth0, float* const out_host[SMK_NPRODUCTS], double sigma_out[SMK_NPRODUCTS]);
+
+/* ---- skewers: batched ReadSpec (make_spectra.py:90-139) over all quasars of one x-slab.
+ * fields[10]: delta, eta_xx, eta_yy, eta_zz, eta_xy, eta_xz, eta_yz, vx, vy, vz; each a float slab
+ * [nxs][ny][nz] holding global x-planes [ix0, ix0+nxs) (halo planes included).  fields[1..6] may be NULL
+ * when rsd == 0, fields[7..9] when dla == 0.
+ * Pixels of quasar q: i in [0, npix_forest[q]) on the global grid rvec[npix] (Mpc/h); pixel i belongs to this
+ * call iff xmin < rvec[i]*X/R <= xmax (make_spectra.py:443-448).  qso_xyzr: 4 doubles per quasar (X,Y,Z,R_QSO).
+ * Outputs are [nqso][npix] float, written only at the pixels owned by this call: delta_l, eta_par,
+ * vpar (before the make_spectra.py:510 rescale); pixels owned but outside the forest get -1e6 / 0 / 0
+ * (make_spectra.py:99-101).  Neighbour indices are clamped to the slab (documented deviation: the reference
+ * gather is unchecked). */
+typedef struct smk_geom {
+  int nx, ny, nz;       /* full box */
+  double dx, dy, dz;    /* cell size */
+  double r0;            /* h*R(z0): distance of the box centre */
+  int dmax;             /* half width of the Gaussian window in cells (3) */
+} smk_geom;
+
+int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs, double xmin,
+                double xmax, int rsd, int dla, int nqso, const double* qso_xyzr, const int* npix_forest,
+                const double* rvec, int npix, float* delta_l, float* eta_par, float* vpar);
+
+/* ---- small-scale field (merge_spectra.py:308-324): delta_s = irfft(rfft(noise) * filt)[:npix] * zscale.
+ * noise: [nqso][nfft] float white noise, or NULL to draw Philox(seed, quasar index).  filt_rows: [nrows][nfft/2+1]
+ * float = sqrt(max(P_miss(z_row,k),0)/pixsize); row_of_qso[q] selects the row (nearest tabulated z to z_eff).
+ * zscale: [nqso][npix] or NULL; when NULL, sig_pix[npix]/sig_eff[q] is used (sigma_s(z)/sigma_s(z_eff)).
+ * nfft must be a power of two in [256, 8192]. */
+int smk_smallscale(smk_ctx* ctx, int nqso, int nfft, int npix, const float* noise, uint64_t seed,
+                   const float* filt_rows, const int* row_of_qso, const float* sig_pix, const float* sig_eff,
+                   float* delta_s);
+
+/* ---- FGPA (util.py:421-433): F = exp(-a exp(b G (delta_l + delta_s + c eta_par))).  a,b,c,G are per-pixel
+ * vectors [npix] (constant when -zfix is used).  delta_s / eta_par may be NULL (treated as 0). */
+int smk_fgpa(smk_ctx* ctx, int nqso, int npix, const float* delta_l, const float* delta_s, const float* eta_par,
+             const float* growthf, const float* a, const float* b, const float* c, float* flux);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMK_H */

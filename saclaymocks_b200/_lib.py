@@ -1,0 +1,74 @@
+"""ctypes binding of libsmk.so (include/smk.h).  There is no CPU fallback: importing a compute entry
+point without the CUDA library raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsmk.so")
+
+NPRODUCTS = 13
+PRODUCT_NAMES = ("boxln_1", "boxln_2", "boxln_3", "box", "eta_xx", "eta_yy", "eta_zz", "eta_xy", "eta_xz", "eta_yz",
+                 "vx", "vy", "vz")
+PRODUCT_ID = {n: i for i, n in enumerate(PRODUCT_NAMES)}
+
+EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy", "smk_boxk_pitch", "smk_boxk_elems",
+           "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
+           "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
+           "smk_make_boxes_host", "smk_skewers", "smk_smallscale", "smk_fgpa")
+
+
+class SmkError(RuntimeError):
+    pass
+
+
+class Geom(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("dx", C.c_double), ("dy", C.c_double),
+                ("dz", C.c_double), ("r0", C.c_double), ("dmax", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libsmk.so (built by saclaymocks_b200.build / __graft_entry__.build); raise if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise SmkError("libsmk.so not built (%s): run `python -m saclaymocks_b200.build`; there is no CPU fallback"
+                       % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i, d, u64, sz = C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_size_t
+    L.smk_last_error.restype = C.c_char_p
+    L.smk_version.restype = i
+    L.smk_ctx_create.argtypes = [C.POINTER(vp), i, i, i, d, i, i, vp]
+    L.smk_ctx_destroy.argtypes = [vp]
+    L.smk_boxk_pitch.argtypes = [vp]
+    L.smk_boxk_elems.argtypes = [vp]
+    L.smk_boxk_elems.restype = sz
+    L.smk_box_elems.argtypes = [vp]
+    L.smk_box_elems.restype = sz
+    L.smk_workspace_bytes.argtypes = [vp]
+    L.smk_workspace_bytes.restype = sz
+    L.smk_sync.argtypes = [vp]
+    L.smk_noise_philox.argtypes = [vp, u64, vp]
+    L.smk_fft_r2c.argtypes = [vp, vp, u64, vp]
+    L.smk_fft_r2c_local.argtypes = [vp, vp, u64, vp]
+    L.smk_fft_r2c_finish.argtypes = [vp, vp, vp]
+    L.smk_synth_c2r.argtypes = [vp, vp, i, vp, i, d, vp, vp]
+    L.smk_synth_c2r_local.argtypes = [vp, vp, i, vp, i, d, vp]
+    L.smk_synth_c2r_finish.argtypes = [vp, vp, vp, vp]
+    L.smk_make_boxes_host.argtypes = [vp, vp, u64, C.POINTER(vp), d, C.POINTER(vp), C.POINTER(d)]
+    L.smk_skewers.argtypes = [vp, C.POINTER(Geom), C.POINTER(vp), i, i, d, d, i, i, i, vp, vp, vp, i, vp, vp, vp]
+    L.smk_smallscale.argtypes = [vp, i, i, i, vp, u64, vp, vp, vp, vp, vp]
+    L.smk_fgpa.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
+    for name in EXPORTS:
+        if name not in ("smk_last_error", "smk_boxk_elems", "smk_box_elems", "smk_workspace_bytes"):
+            getattr(L, name).restype = i
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise SmkError("libsmk error %d: %s" % (rc, lib().smk_last_error().decode()))

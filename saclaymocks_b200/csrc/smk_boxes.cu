@@ -1,0 +1,391 @@
+// 3-D r2c / c2r FFT passes with fused prologues/epilogues for the GRF box synthesis
+// (replaces pyfftw.FFTW(...).execute() + the numpy passes around it in bin/make_boxes.py:40-125,
+// 242-431).  All passes are HBM-bound: each reads and writes the box once.
+//
+//   strided complex pass (x or y axis): tile = LINES consecutive kz columns x N points in shared
+//     memory as [point][line]; the first DIF stage reads straight from global memory (rows of
+//     LINES complex = 128 B) with the spectral-weight / k-factor multiply fused into the load, the
+//     last stage writes straight to global memory in natural order.
+//   contiguous pass (z axis): tile = LINES lines x (NZ/2+1) complex as [line][point] with odd
+//     pitch; half-length complex FFT + real-transform pre/post step; the inverse fuses /N, sum and
+//     sum of squares (for sigma) into the store, the forward fuses Philox noise into the load.
+#include <math.h>
+#include <stdio.h>
+
+#include "smk_fft.cuh"
+#include "smk_internal.h"
+#include "smk_philox.cuh"
+
+namespace smk {
+
+// ------------------------------------------------------------------ strided complex pass
+template <int N>
+struct StridedTraits {
+  static constexpr int LINES = (N > 1024) ? 8 : 16;
+  static constexpr int NT_ = LINES * N / 32;
+  static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
+};
+
+struct StridedParams {
+  const float2* in;
+  float2* out;
+  PassAddr ain, aout;
+  int ncols;
+  MulArgs mul;
+  const float2* tw;
+};
+
+__device__ __forceinline__ long long point_off(const PassAddr& a, int n) {
+  int hi = n / a.nsplit;
+  int lo = n - hi * a.nsplit;
+  return hi * a.hi_stride + lo * a.lo_stride;
+}
+
+// factor of make_boxes.py:299-306,324-429 in the reference's float32 rounding order
+template <int MUL>
+__device__ __forceinline__ float2 apply_mul(float2 v, const MulArgs& m, int n, int outer, int col, long long in_off,
+                                            bool col_ok) {
+  if (MUL == MUL_NONE) return v;
+  if (MUL == MUL_TABLE) {
+    float w = col_ok ? __ldg(m.wt + n * m.wt_n_stride + outer * m.wt_outer_stride + col) : 0.f;
+    v = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
+    if (m.store_back != nullptr && col_ok) m.store_back[in_off] = v;
+    return v;
+  }
+  float kx = __ldg(m.kn + n), ky = __ldg(m.ko + outer + m.outer0), kz = col_ok ? __ldg(m.kc + col) : 0.f;
+  float kk = __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
+  if (n == 0 && outer + m.outer0 == 0 && col == 0) kk = 1.f;
+  float ka = m.fa == 0 ? kx : (m.fa == 1 ? ky : kz);
+  float kb = m.fb == 0 ? kx : (m.fb == 1 ? ky : kz);
+  if (MUL == MUL_ETA) {
+    float f = __fdiv_rn(__fmul_rn(ka, kb), kk);
+    return make_float2(__fmul_rn(v.x, f), __fmul_rn(v.y, f));
+  }
+  // MUL_VEL: boxk *= -1j*k/kk*H0*dgrowth0 -- float32 up to "*H0", then float64 (numpy promotes on the
+  // float64 scalar dgrowth0 and rounds the complex128 product back to complex64)
+  float f32 = __fmul_rn(__fdiv_rn(-ka, kk), 100.0f);
+  double f = (double)f32 * m.vscale;   // vscale = dgrowth0 (H0 = 100 is applied above in float32)
+  return make_float2((float)(-(double)v.y * f), (float)((double)v.x * f));
+}
+
+template <int N, bool INV, int MUL>
+__global__ void __launch_bounds__(StridedTraits<N>::NT) c2c_strided_kernel(StridedParams p) {
+  using P = typename PlanFor<N>::type;
+  constexpr int LINES = StridedTraits<N>::LINES;
+  constexpr int NT = StridedTraits<N>::NT;
+  extern __shared__ float2 sm[];   // [N][LINES]
+  const int col0 = blockIdx.x * LINES;
+  const int outer = blockIdx.y;
+  const long long ibase = outer * p.ain.outer_stride + col0;
+  const long long obase = outer * p.aout.outer_stride + col0;
+  const int ncols = p.ncols;
+
+  auto ld_g = [&](int line, int n) {
+    long long off = ibase + point_off(p.ain, n) + line;
+    bool ok = (col0 + line) < ncols;
+    float2 v = ok ? p.in[off] : make_float2(0.f, 0.f);
+    return apply_mul<MUL>(v, p.mul, n, outer, col0 + line, off, ok);
+  };
+  auto st_g = [&](int line, int k, float2 val) {
+    if ((col0 + line) < ncols) p.out[obase + point_off(p.aout, k) + line] = val;
+  };
+  auto st_s = [&](int line, int pos, float2 val) { sm[pos * LINES + line] = val; };
+  auto ld_s = [&](int line, int pos) { return sm[pos * LINES + line]; };
+
+  if constexpr (P::S == 1) {
+    dif_stage<P, 0, INV, LINES, NT, OUT_NATURAL>(ld_g, st_g, p.tw, 1);
+  } else {
+    dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE>(ld_g, st_s, p.tw, 1);
+    __syncthreads();
+    dif_stages_smem<P, 1, P::S - 1, INV, LINES, 1, LINES, NT>(sm, p.tw, 1);
+    dif_stage<P, P::S - 1, INV, LINES, NT, OUT_NATURAL>(ld_s, st_g, p.tw, 1);
+  }
+}
+
+template <int N, bool INV, int MUL>
+static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st) {
+  constexpr int LINES = StridedTraits<N>::LINES;
+  constexpr int NT = StridedTraits<N>::NT;
+  size_t smem = (size_t)N * LINES * sizeof(float2);
+  auto kern = c2c_strided_kernel<N, INV, MUL>;
+  if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p.ncols + LINES - 1) / LINES, nouter);
+  kern<<<grid, NT, smem, st>>>(p);
+  SMK_CUDA_OK(cudaGetLastError());
+  return SMK_OK;
+}
+
+template <int N>
+static int launch_strided_n(bool inv, int mul, const StridedParams& p, int nouter, cudaStream_t st) {
+  if (!inv) {
+    if (mul != MUL_NONE) { set_error("forward pass takes no multiplier"); return SMK_ERR_ARG; }
+    return launch_strided_t<N, false, MUL_NONE>(p, nouter, st);
+  }
+  switch (mul) {
+    case MUL_NONE: return launch_strided_t<N, true, MUL_NONE>(p, nouter, st);
+    case MUL_TABLE: return launch_strided_t<N, true, MUL_TABLE>(p, nouter, st);
+    case MUL_ETA: return launch_strided_t<N, true, MUL_ETA>(p, nouter, st);
+    case MUL_VEL: return launch_strided_t<N, true, MUL_VEL>(p, nouter, st);
+  }
+  set_error("bad multiplier mode");
+  return SMK_ERR_ARG;
+}
+
+#define SMK_STRIDED_SIZES(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2560)
+
+bool strided_size_supported(int n) {
+#define X(N_) if (n == N_) return true;
+  SMK_STRIDED_SIZES(X)
+#undef X
+  return false;
+}
+
+int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, float2* out, PassAddr ain, PassAddr aout,
+                       int nouter, int ncols, const MulArgs& mul, const float2* tw, cudaStream_t st) {
+  StridedParams p{in, out, ain, aout, ncols, mul, tw};
+  switch (N) {
+#define X(N_) case N_: return launch_strided_n<N_>(inverse, mul_mode, p, nouter, st);
+    SMK_STRIDED_SIZES(X)
+#undef X
+  }
+  set_error("unsupported x/y length " + std::to_string(N));
+  return SMK_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------ contiguous (z) pass
+template <int M>
+struct ZTraits {
+  static constexpr int LINES = (M > 1024) ? 4 : 16;
+  static constexpr int NT_ = (M % 3 == 0) ? LINES * M / 48 / 32 * 32 : LINES * M / 32;
+  static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
+  static constexpr int LP = M + 1;   // odd pitch: column accesses (lane = line) are conflict free
+};
+
+struct R2CParams {
+  const float* in;
+  float2* out;
+  long long nlines;
+  int pitch;
+  const float2* tw;   // W_NZ
+  uint64_t seed;
+  long long cell0;    // global index of the first cell of line 0 (Philox counter base)
+};
+
+template <int M, bool PHILOX>
+__global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
+  using P = typename PlanFor<M>::type;
+  constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = ZTraits<M>::LP;
+  extern __shared__ float2 sm[];   // [LINES][LP]
+  const long long line0 = (long long)blockIdx.x * LINES;
+  // ---- load (or draw) the real lines as M float2 each
+  if (PHILOX) {
+    // one Philox call -> 4 normals = 2 float2 = cells 4c..4c+3 of the line (M is even)
+    for (int idx = threadIdx.x; idx < LINES * (M / 2); idx += NT) {
+      int line = idx / (M / 2), c = idx - line * (M / 2);
+      if (line0 + line < p.nlines) {
+        long long cell = p.cell0 + (line0 + line) * (2LL * M) + 4LL * c;
+        float4 g = philox_normal4(p.seed, (uint64_t)cell >> 2);
+        sm[line * LP + 2 * c] = make_float2(g.x, g.y);
+        sm[line * LP + 2 * c + 1] = make_float2(g.z, g.w);
+      }
+    }
+  } else {
+    const float2* in2 = reinterpret_cast<const float2*>(p.in);
+    for (int idx = threadIdx.x; idx < LINES * M; idx += NT) {
+      int line = idx / M, n = idx - line * M;
+      if (line0 + line < p.nlines) sm[line * LP + n] = __ldg(in2 + (line0 + line) * M + n);
+    }
+  }
+  __syncthreads();
+  // ---- M-point complex FFT of z[n] = x[2n] + i x[2n+1], output re-sorted to natural order
+  dif_stages_smem<P, 0, P::S - 1, false, LINES, LP, 1, NT>(sm, p.tw, 2);
+  dif_last_resort_smem<P, false, LINES, LP, 1, NT>(sm, p.tw, 2);
+  // ---- X[k] = (Z[k]+conj(Z[M-k]))/2 - (i/2) w^k (Z[k]-conj(Z[M-k])),  k = 0..M  (pairs k, M-k in place)
+  for (int task = threadIdx.x; task < LINES * (M / 2 + 1); task += NT) {
+    int line = task % LINES, k = task / LINES;
+    float2* row = sm + line * LP;
+    float2 a = row[k], b = (k == 0) ? a : row[M - k];
+    float2 w = __ldg(p.tw + k);                       // exp(-2 pi i k / NZ)
+    float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));   // (a + conj b)/2
+    float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));   // (a - conj b)/2
+    float2 t = cmul(w, d);
+    float2 mit = make_float2(t.y, -t.x);              // -i t
+    float2 xk = cadd(e, mit);
+    // X[M-k] = conj(e) - (-i conj(w)... ) : derived from the same e, d:  conj(e) + conj(-i t)... = conj(e) - conj(mit)
+    float2 xm = make_float2(e.x - mit.x, -e.y + mit.y);
+    row[k] = xk;
+    if (k != M - k) row[M - k] = xm;
+  }
+  __syncthreads();
+  // ---- store M+1 complex per line
+  for (int idx = threadIdx.x; idx < LINES * (M + 1); idx += NT) {
+    int line = idx / (M + 1), k = idx - line * (M + 1);
+    if (line0 + line < p.nlines) p.out[(line0 + line) * p.pitch + k] = sm[line * LP + k];
+  }
+}
+
+struct C2RParams {
+  const float2* in;
+  float* out;
+  long long nlines;
+  int pitch;
+  const float2* tw;
+  float norm;       // nx*ny*nz as float (the reference divides: box /= NX*NY*NZ)
+  double* stats;    // [2] sum, sum of squares (atomically accumulated) or null
+};
+
+template <int M>
+__global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
+  using P = typename PlanFor<M>::type;
+  constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = ZTraits<M>::LP;
+  extern __shared__ float2 sm[];
+  __shared__ double red[2][NT / 32];
+  const long long line0 = (long long)blockIdx.x * LINES;
+  for (int idx = threadIdx.x; idx < LINES * (M + 1); idx += NT) {
+    int line = idx / (M + 1), k = idx - line * (M + 1);
+    float2 v = make_float2(0.f, 0.f);
+    if (line0 + line < p.nlines) v = __ldg(p.in + (line0 + line) * p.pitch + k);
+    sm[line * LP + k] = v;
+  }
+  __syncthreads();
+  // ---- Z[k] = A + iB, A = X[k] + conj(X[M-k]), B = (X[k] - conj(X[M-k])) w^-k ; imaginary parts of the
+  //      DC and Nyquist bins are ignored, as FFTW's / pocketfft's c2r do
+  for (int task = threadIdx.x; task < LINES * (M / 2 + 1); task += NT) {
+    int line = task % LINES, k = task / LINES;
+    float2* row = sm + line * LP;
+    float2 a = row[k], b = row[M - k];
+    if (k == 0) { a.y = 0.f; b.y = 0.f; }
+    float2 w = __ldg(p.tw + k);
+    w.y = -w.y;                                        // exp(+2 pi i k / NZ)
+    float2 A = make_float2(a.x + b.x, a.y - b.y);
+    float2 B = cmul(make_float2(a.x - b.x, a.y + b.y), w);
+    float2 zk = make_float2(A.x - B.y, A.y + B.x);     // A + iB
+    float2 zm = make_float2(A.x + B.y, -A.y + B.x);    // conj(A) + i conj(B)
+    row[k] = zk;
+    if (k != 0 && k != M - k) row[M - k] = zm;
+  }
+  __syncthreads();
+  dif_stages_smem<P, 0, P::S - 1, true, LINES, LP, 1, NT>(sm, p.tw, 2);
+  dif_last_resort_smem<P, true, LINES, LP, 1, NT>(sm, p.tw, 2);
+  // ---- store x[2n], x[2n+1] = z[n] / N, accumulate sum and sum of squares
+  float s1 = 0.f, s2 = 0.f;
+  float2* out2 = reinterpret_cast<float2*>(p.out);
+  for (int idx = threadIdx.x; idx < LINES * M; idx += NT) {
+    int line = idx / M, n = idx - line * M;
+    if (line0 + line < p.nlines) {
+      float2 z = sm[line * LP + n];
+      z.x = __fdiv_rn(z.x, p.norm);
+      z.y = __fdiv_rn(z.y, p.norm);
+      out2[(line0 + line) * M + n] = z;
+      s1 += z.x + z.y;
+      s2 += z.x * z.x + z.y * z.y;
+    }
+  }
+  if (p.stats != nullptr) {
+    double d1 = s1, d2 = s2;
+    for (int o = 16; o > 0; o >>= 1) {
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = d1; red[1][warp] = d2; }
+    __syncthreads();
+    if (warp == 0) {
+      d1 = lane < NT / 32 ? red[0][lane] : 0.0;
+      d2 = lane < NT / 32 ? red[1][lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) {
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+      }
+      if (lane == 0) { atomicAdd(p.stats, d1); atomicAdd(p.stats + 1, d2); }
+    }
+  }
+}
+
+#define SMK_Z_HALF_SIZES(X) X(4) X(8) X(12) X(16) X(32) X(48) X(64) X(128) X(256) X(512) X(768)
+
+bool z_size_supported(int nz) {
+#define X(M_) if (nz == 2 * M_) return true;
+  SMK_Z_HALF_SIZES(X)
+#undef X
+  return false;
+}
+
+template <int M>
+static int launch_r2c_t(const R2CParams& p, bool philox, cudaStream_t st) {
+  size_t smem = (size_t)ZTraits<M>::LINES * ZTraits<M>::LP * sizeof(float2);
+  unsigned grid = (unsigned)((p.nlines + ZTraits<M>::LINES - 1) / ZTraits<M>::LINES);
+  if (philox) {
+    auto kern = r2c_z_kernel<M, true>;
+    if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, ZTraits<M>::NT, smem, st>>>(p);
+  } else {
+    auto kern = r2c_z_kernel<M, false>;
+    if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, ZTraits<M>::NT, smem, st>>>(p);
+  }
+  SMK_CUDA_OK(cudaGetLastError());
+  return SMK_OK;
+}
+
+int launch_r2c_z(int NZ, const float* in, float2* out, long long nlines, int pitch, const float2* tw, bool philox,
+                 uint64_t seed, long long cell0, cudaStream_t st) {
+  R2CParams p{in, out, nlines, pitch, tw, seed, cell0};
+  switch (NZ / 2) {
+#define X(M_) case M_: return launch_r2c_t<M_>(p, philox, st);
+    SMK_Z_HALF_SIZES(X)
+#undef X
+  }
+  set_error("unsupported z length " + std::to_string(NZ));
+  return SMK_ERR_UNSUPPORTED;
+}
+
+template <int M>
+static int launch_c2r_t(const C2RParams& p, cudaStream_t st) {
+  size_t smem = (size_t)ZTraits<M>::LINES * ZTraits<M>::LP * sizeof(float2);
+  unsigned grid = (unsigned)((p.nlines + ZTraits<M>::LINES - 1) / ZTraits<M>::LINES);
+  auto kern = c2r_z_kernel<M>;
+  if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, ZTraits<M>::NT, smem, st>>>(p);
+  SMK_CUDA_OK(cudaGetLastError());
+  return SMK_OK;
+}
+
+int launch_c2r_z(int NZ, const float2* in, float* out, long long nlines, int pitch, const float2* tw, float norm,
+                 double* stats, cudaStream_t st) {
+  C2RParams p{in, out, nlines, pitch, tw, norm, stats};
+  switch (NZ / 2) {
+#define X(M_) case M_: return launch_c2r_t<M_>(p, st);
+    SMK_Z_HALF_SIZES(X)
+#undef X
+  }
+  set_error("unsupported z length " + std::to_string(NZ));
+  return SMK_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------ stand-alone Philox fill
+__global__ void philox_fill_kernel(float* out, long long ncells, uint64_t seed, long long cell0) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; 4 * q < ncells; q += stride) {
+    float4 g = philox_normal4(seed, (uint64_t)(cell0 + 4 * q) >> 2);
+    if (4 * q + 3 < ncells) {
+      reinterpret_cast<float4*>(out)[q] = g;
+    } else {
+      float t[4] = {g.x, g.y, g.z, g.w};
+      for (int i = 0; 4 * q + i < ncells; ++i) out[4 * q + i] = t[i];
+    }
+  }
+}
+
+int launch_philox_fill(float* out, long long ncells, uint64_t seed, long long cell0, cudaStream_t st) {
+  if (cell0 % 4 != 0) { set_error("philox fill: slab offset must be a multiple of 4 cells"); return SMK_ERR_ARG; }
+  long long nq = (ncells + 3) / 4;
+  int blocks = (int)((nq + 255) / 256 < 148 * 16 ? (nq + 255) / 256 : 148 * 16);
+  if (blocks < 1) blocks = 1;
+  philox_fill_kernel<<<blocks, 256, 0, st>>>(out, ncells, seed, cell0);
+  SMK_CUDA_OK(cudaGetLastError());
+  return SMK_OK;
+}
+
+}  // namespace smk

@@ -1,0 +1,269 @@
+// C ABI of libsmk.so (include/smk.h): context, plans, and the box-synthesis entry points.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "smk_internal.h"
+
+namespace smk {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace smk
+
+using namespace smk;
+
+struct smk_ctx {
+  int nx, ny, nz, nzh, pitch;
+  int rank, nranks, nxl, nyl;
+  double dcell;
+  cudaStream_t stream;
+  float2 *tw_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
+  float *kx = nullptr, *ky = nullptr, *kz = nullptr;
+  float2* work = nullptr;      // [nxl][ny][pitch] (== boxk size)
+  double* stats = nullptr;     // scratch for the host wrapper
+  size_t bytes = 0;
+};
+
+static int make_twiddles(int n, float2** dptr, size_t* bytes) {
+  std::vector<float2> h(n);
+  for (int k = 0; k < n; ++k) {
+    double a = -2.0 * M_PI * (double)k / (double)n;
+    h[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  SMK_CUDA_OK(cudaMalloc(dptr, n * sizeof(float2)));
+  SMK_CUDA_OK(cudaMemcpy(*dptr, h.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+  *bytes += n * sizeof(float2);
+  return SMK_OK;
+}
+
+// np.float32(np.fft.fftfreq(n) * 2 * k_ny) / rfftfreq -- make_boxes.py:299-304
+static int make_ktable(int n, bool rfft, double dcell, float** dptr, size_t* bytes) {
+  double k_ny = M_PI / dcell;
+  int len = rfft ? n / 2 + 1 : n;
+  std::vector<float> h(len);
+  for (int i = 0; i < len; ++i) {
+    double f;
+    if (rfft) f = (double)i / ((double)n * 1.0);
+    else f = (double)((i < (n + 1) / 2) ? i : i - n) / ((double)n * 1.0);
+    h[i] = (float)(f * 2 * k_ny);
+  }
+  SMK_CUDA_OK(cudaMalloc(dptr, len * sizeof(float)));
+  SMK_CUDA_OK(cudaMemcpy(*dptr, h.data(), len * sizeof(float), cudaMemcpyHostToDevice));
+  *bytes += len * sizeof(float);
+  return SMK_OK;
+}
+
+extern "C" {
+
+const char* smk_last_error(void) { return g_err.c_str(); }
+int smk_version(void) { return 100; }
+
+int smk_ctx_create(smk_ctx** out, int nx, int ny, int nz, double dcell, int rank, int nranks, void* stream) {
+  if (!out || nx <= 0 || ny <= 0 || nz <= 0 || nranks < 1 || rank < 0 || rank >= nranks) {
+    set_error("smk_ctx_create: bad argument");
+    return SMK_ERR_ARG;
+  }
+  if (!strided_size_supported(nx) || !strided_size_supported(ny) || !z_size_supported(nz)) {
+    set_error("smk_ctx_create: unsupported box dimensions " + std::to_string(nx) + "x" + std::to_string(ny) + "x" +
+              std::to_string(nz));
+    return SMK_ERR_UNSUPPORTED;
+  }
+  if (nx % nranks || ny % nranks) {
+    set_error("smk_ctx_create: nx and ny must be divisible by nranks");
+    return SMK_ERR_ARG;
+  }
+  smk_ctx* c = new smk_ctx();
+  c->nx = nx; c->ny = ny; c->nz = nz; c->nzh = nz / 2 + 1;
+  c->pitch = (c->nzh + 15) / 16 * 16;
+  c->rank = rank; c->nranks = nranks; c->nxl = nx / nranks; c->nyl = ny / nranks;
+  c->dcell = dcell;
+  c->stream = (cudaStream_t)stream;
+  int rc;
+  if ((rc = make_twiddles(nx, &c->tw_x, &c->bytes))) return rc;
+  if ((rc = make_twiddles(ny, &c->tw_y, &c->bytes))) return rc;
+  if ((rc = make_twiddles(nz, &c->tw_z, &c->bytes))) return rc;
+  if ((rc = make_ktable(nx, false, dcell, &c->kx, &c->bytes))) return rc;
+  if ((rc = make_ktable(ny, false, dcell, &c->ky, &c->bytes))) return rc;
+  if ((rc = make_ktable(nz, true, dcell, &c->kz, &c->bytes))) return rc;
+  size_t wbytes = (size_t)c->nxl * ny * c->pitch * sizeof(float2);
+  SMK_CUDA_OK(cudaMalloc(&c->work, wbytes));
+  c->bytes += wbytes;
+  SMK_CUDA_OK(cudaMalloc(&c->stats, 2 * SMK_NPRODUCTS * sizeof(double)));
+  *out = c;
+  return SMK_OK;
+}
+
+int smk_ctx_destroy(smk_ctx* c) {
+  if (!c) return SMK_OK;
+  cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->tw_z);
+  cudaFree(c->kx); cudaFree(c->ky); cudaFree(c->kz);
+  cudaFree(c->work); cudaFree(c->stats);
+  delete c;
+  return SMK_OK;
+}
+
+int smk_boxk_pitch(const smk_ctx* c) { return c->pitch; }
+size_t smk_boxk_elems(const smk_ctx* c) { return (size_t)c->nx * c->nyl * c->pitch; }
+size_t smk_box_elems(const smk_ctx* c) { return (size_t)c->nxl * c->ny * c->nz; }
+size_t smk_workspace_bytes(const smk_ctx* c) { return c->bytes; }
+int smk_sync(smk_ctx* c) {
+  SMK_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return SMK_OK;
+}
+
+int smk_noise_philox(smk_ctx* c, uint64_t seed, float* box_slab) {
+  long long ncells = (long long)c->nxl * c->ny * c->nz;
+  return launch_philox_fill(box_slab, ncells, seed, (long long)c->rank * ncells, c->stream);
+}
+
+// ---- forward
+int smk_fft_r2c_local(smk_ctx* c, const float* box_slab, uint64_t seed, void* sendbuf) {
+  long long nlines = (long long)c->nxl * c->ny;
+  long long cell0 = (long long)c->rank * nlines * c->nz;
+  float2* tmp = (c->nranks == 1) ? (float2*)sendbuf : c->work;
+  int rc = launch_r2c_z(c->nz, box_slab, tmp, nlines, c->pitch, c->tw_z, box_slab == nullptr, seed, cell0, c->stream);
+  if (rc) return rc;
+  // y pass: outer = local x plane; output into [dest][xl][yl][z] (dest = y / nyl)
+  PassAddr ain{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
+  PassAddr aout{(long long)c->nyl * c->pitch, (long long)c->nxl * c->nyl * c->pitch, (long long)c->pitch, c->nyl};
+  MulArgs m{};
+  return launch_c2c_strided(c->ny, false, MUL_NONE, tmp, (float2*)sendbuf, ain, aout, c->nxl, c->pitch, m, c->tw_y,
+                            c->stream);
+}
+
+int smk_fft_r2c_finish(smk_ctx* c, const void* recvbuf, void* boxk) {
+  // x pass on [nx][nyl][pitch]: outer = local y
+  PassAddr a{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
+  MulArgs m{};
+  return launch_c2c_strided(c->nx, false, MUL_NONE, (const float2*)recvbuf, (float2*)boxk, a, a, c->nyl, c->pitch, m,
+                            c->tw_x, c->stream);
+}
+
+int smk_fft_r2c(smk_ctx* c, const float* box_slab, uint64_t seed, void* boxk) {
+  if (c->nranks != 1) { set_error("smk_fft_r2c: single-rank entry point; use _local/_finish"); return SMK_ERR_ARG; }
+  int rc = smk_fft_r2c_local(c, box_slab, seed, boxk);
+  if (rc) return rc;
+  return smk_fft_r2c_finish(c, boxk, boxk);
+}
+
+// ---- inverse
+int smk_synth_c2r_local(smk_ctx* c, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
+                        void* sendbuf) {
+  if (product < 0 || product >= SMK_NPRODUCTS) { set_error("bad product id"); return SMK_ERR_ARG; }
+  MulArgs m{};
+  int mode;
+  if (product <= SMK_P0) {
+    if (!wtable) { set_error("spectral weight table required for products PLN1..P0"); return SMK_ERR_ARG; }
+    mode = MUL_TABLE;
+    m.wt = wtable;
+    m.wt_n_stride = (long long)c->nyl * c->nzh;
+    m.wt_outer_stride = c->nzh;
+    m.store_back = (product == SMK_P0 && store_p0) ? (float2*)boxk : nullptr;
+  } else {
+    static const int FA[] = {0, 1, 2, 0, 0, 1, 0, 1, 2};
+    static const int FB[] = {0, 1, 2, 1, 2, 2, 0, 0, 0};
+    mode = product >= SMK_VX ? MUL_VEL : MUL_ETA;
+    m.kn = c->kx; m.ko = c->ky; m.kc = c->kz;
+    m.outer0 = c->rank * c->nyl;
+    m.fa = FA[product - SMK_ETA_XX];
+    m.fb = FB[product - SMK_ETA_XX];
+    m.vscale = dgrowth0;
+  }
+  PassAddr a{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
+  return launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, (float2*)sendbuf, a, a, c->nyl, c->nzh, m, c->tw_x,
+                            c->stream);
+}
+
+int smk_synth_c2r_finish(smk_ctx* c, void* recvbuf, float* out_slab, double* stats) {
+  // y pass: input [src][xl][yl][z] (y = src*nyl + yl), output [xl][ny][pitch]
+  PassAddr ain{(long long)c->nyl * c->pitch, (long long)c->nxl * c->nyl * c->pitch, (long long)c->pitch, c->nyl};
+  PassAddr aout{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
+  float2* tmp = (c->nranks == 1) ? (float2*)recvbuf : c->work;
+  MulArgs m{};
+  int rc = launch_c2c_strided(c->ny, true, MUL_NONE, (const float2*)recvbuf, tmp, ain, aout, c->nxl, c->nzh, m,
+                              c->tw_y, c->stream);
+  if (rc) return rc;
+  float norm = (float)((double)c->nx * c->ny * c->nz);
+  return launch_c2r_z(c->nz, tmp, out_slab, (long long)c->nxl * c->ny, c->pitch, c->tw_z, norm, stats, c->stream);
+}
+
+int smk_synth_c2r(smk_ctx* c, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
+                  float* out_slab, double* stats) {
+  if (c->nranks != 1) { set_error("smk_synth_c2r: single-rank entry point; use _local/_finish"); return SMK_ERR_ARG; }
+  int rc = smk_synth_c2r_local(c, boxk, product, wtable, store_p0, dgrowth0, c->work);
+  if (rc) return rc;
+  return smk_synth_c2r_finish(c, c->work, out_slab, stats);
+}
+
+int smk_make_boxes_host(smk_ctx* c, const float* noise_host, uint64_t seed, const float* const wtables_host[4],
+                        double dgrowth0, float* const out_host[SMK_NPRODUCTS], double sigma_out[SMK_NPRODUCTS]) {
+  if (c->nranks != 1) { set_error("smk_make_boxes_host: single rank only"); return SMK_ERR_ARG; }
+  size_t ncell = (size_t)c->nx * c->ny * c->nz, nk = smk_boxk_elems(c), nw = (size_t)c->nx * c->ny * c->nzh;
+  float2* boxk = nullptr;
+  float* wt = nullptr;
+  float* box[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream;
+  cudaEvent_t done[2], copied[2];
+  SMK_CUDA_OK(cudaMalloc(&boxk, nk * sizeof(float2)));
+  SMK_CUDA_OK(cudaMalloc(&wt, nw * sizeof(float)));
+  SMK_CUDA_OK(cudaMalloc(&box[0], ncell * sizeof(float)));
+  SMK_CUDA_OK(cudaMalloc(&box[1], ncell * sizeof(float)));
+  SMK_CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    SMK_CUDA_OK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    SMK_CUDA_OK(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+  }
+  SMK_CUDA_OK(cudaMemsetAsync(boxk, 0, nk * sizeof(float2), c->stream));
+  SMK_CUDA_OK(cudaMemsetAsync(c->stats, 0, 2 * SMK_NPRODUCTS * sizeof(double), c->stream));
+  int rc = SMK_OK;
+  if (noise_host) {
+    SMK_CUDA_OK(cudaMemcpyAsync(box[0], noise_host, ncell * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = smk_fft_r2c(c, box[0], seed, boxk);
+  } else {
+    rc = smk_fft_r2c(c, nullptr, seed, boxk);
+  }
+  int nb = 0;
+  for (int p = 0; p < SMK_NPRODUCTS && rc == SMK_OK; ++p) {
+    bool need_p0 = (p == SMK_P0);           // boxk must become boxk*P0 for every later product
+    if (!out_host[p] && !need_p0) continue;
+    if (p <= SMK_P0) {
+      if (!wtables_host || !wtables_host[p]) { set_error("missing weight table"); rc = SMK_ERR_ARG; break; }
+      SMK_CUDA_OK(cudaMemcpyAsync(wt, wtables_host[p], nw * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    int b = nb & 1;
+    SMK_CUDA_OK(cudaStreamWaitEvent(c->stream, copied[b], 0));     // buffer free again?
+    rc = smk_synth_c2r(c, boxk, p, wt, 1, dgrowth0, box[b], c->stats + 2 * p);
+    if (rc) break;
+    SMK_CUDA_OK(cudaEventRecord(done[b], c->stream));
+    if (out_host[p]) {
+      SMK_CUDA_OK(cudaStreamWaitEvent(copy_stream, done[b], 0));
+      SMK_CUDA_OK(cudaMemcpyAsync(out_host[p], box[b], ncell * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+      SMK_CUDA_OK(cudaEventRecord(copied[b], copy_stream));
+    }
+    ++nb;
+  }
+  double hstats[2 * SMK_NPRODUCTS];
+  cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(copy_stream);
+  cudaMemcpy(hstats, c->stats, sizeof(hstats), cudaMemcpyDeviceToHost);
+  cudaFree(boxk); cudaFree(wt); cudaFree(box[0]); cudaFree(box[1]);
+  cudaStreamDestroy(copy_stream);
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(done[i]); cudaEventDestroy(copied[i]); }
+  if (rc) return rc;
+  SMK_CUDA_OK(e1);
+  SMK_CUDA_OK(e2);
+  for (int p = 0; p < SMK_NPRODUCTS; ++p) {
+    double s1 = hstats[2 * p], s2 = hstats[2 * p + 1], n = (double)ncell;
+    double var = s2 / n - (s1 / n) * (s1 / n);
+    if (sigma_out) sigma_out[p] = var > 0 ? sqrt(var) : 0.0;
+    if ((out_host[p] || p == SMK_P0) && (!(s2 > 0.0) || isnan(s2))) {
+      set_error("box " + std::to_string(p) + " is null or NaN");   // make_boxes.py:100-105
+      return SMK_ERR_NULL_BOX;
+    }
+  }
+  return SMK_OK;
+}
+
+}  // extern "C"
+
+cudaStream_t smk_ctx_stream(const smk_ctx* ctx) { return ctx ? ctx->stream : (cudaStream_t)0; }

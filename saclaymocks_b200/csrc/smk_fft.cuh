@@ -1,0 +1,267 @@
+// Shared-memory-staged mixed-radix FFT building blocks (sm_100a).
+//
+// Every 1-D transform of the hot path (make_boxes.py:53,87; merge_spectra.py:311,321 in the
+// reference, done there by FFTW) is computed here as an in-place decimation-in-frequency
+// FFT on a tile of LINES independent lines held in shared memory.  Threads map to
+// (line, butterfly) with the line index fastest, so that all lanes of a half-warp execute the
+// SAME butterfly on DIFFERENT lines: every shared-memory access of a stage is then a row of
+// consecutive float2 (strided passes, layout [point][line]) or a column with odd pitch
+// (contiguous pass, layout [line][point], pitch M+1) -- conflict free for any index pattern,
+// which is what lets the digit-reversed in-place algorithm be used without transposes.
+// Twiddles are float2 tables computed in fp64 on the host (W[k] = exp(-2 pi i k / N)).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smk {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 mul_mi(float2 a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+// ---------------------------------------------------------------- radix butterflies
+// y_q = sum_t x_t w^(t q),  w = exp(-2 pi i / R) (forward) or its conjugate (INV)
+template <int R, bool INV>
+struct Butterfly;
+
+template <bool INV>
+struct Butterfly<2, INV> {
+  static __device__ __forceinline__ void run(float2 (&v)[2]) {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+};
+
+template <bool INV>
+struct Butterfly<3, INV> {
+  static __device__ __forceinline__ void run(float2 (&v)[3]) {
+    const float S3 = 0.86602540378443864676f;
+    float2 s = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+    float2 m = make_float2(v[0].x - 0.5f * s.x, v[0].y - 0.5f * s.y);
+    float2 n = mul_mi<INV>(cscale(d, S3));   // -i n (fwd), +i n (inv)
+    v[0] = cadd(v[0], s);
+    v[1] = cadd(m, n);
+    v[2] = csub(m, n);
+  }
+};
+
+template <bool INV>
+struct Butterfly<4, INV> {
+  static __device__ __forceinline__ void run(float2 (&v)[4]) {
+    float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+    float2 t2 = cadd(v[1], v[3]), t3 = mul_mi<INV>(csub(v[1], v[3]));
+    v[0] = cadd(t0, t2);
+    v[2] = csub(t0, t2);
+    v[1] = cadd(t1, t3);
+    v[3] = csub(t1, t3);
+  }
+};
+
+template <bool INV>
+struct Butterfly<5, INV> {
+  static __device__ __forceinline__ void run(float2 (&v)[5]) {
+    const float C1 = 0.30901699437494742410f, C2 = -0.80901699437494742410f;
+    const float S1 = 0.95105651629515357212f, S2 = 0.58778525229247312917f;
+    float2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
+    float2 b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+    float2 m1 = make_float2(v[0].x + C1 * a1.x + C2 * a2.x, v[0].y + C1 * a1.y + C2 * a2.y);
+    float2 m2 = make_float2(v[0].x + C2 * a1.x + C1 * a2.x, v[0].y + C2 * a1.y + C1 * a2.y);
+    float2 n1 = mul_mi<INV>(make_float2(S1 * b1.x + S2 * b2.x, S1 * b1.y + S2 * b2.y));
+    float2 n2 = mul_mi<INV>(make_float2(S2 * b1.x - S1 * b2.x, S2 * b1.y - S1 * b2.y));
+    v[0] = cadd(v[0], cadd(a1, a2));
+    v[1] = cadd(m1, n1);
+    v[4] = csub(m1, n1);
+    v[2] = cadd(m2, n2);
+    v[3] = csub(m2, n2);
+  }
+};
+
+template <bool INV>
+struct Butterfly<8, INV> {
+  static __device__ __forceinline__ void run(float2 (&v)[8]) {
+    const float H = 0.70710678118654752440f;
+    float2 e[4] = {v[0], v[2], v[4], v[6]};
+    float2 o[4] = {v[1], v[3], v[5], v[7]};
+    Butterfly<4, INV>::run(e);
+    Butterfly<4, INV>::run(o);
+    // o_q *= w8^q
+    float2 o1 = INV ? make_float2((o[1].x - o[1].y) * H, (o[1].x + o[1].y) * H)
+                    : make_float2((o[1].x + o[1].y) * H, (o[1].y - o[1].x) * H);
+    float2 o2 = mul_mi<INV>(o[2]);
+    float2 o3 = INV ? make_float2((-o[3].x - o[3].y) * H, (o[3].x - o[3].y) * H)
+                    : make_float2((o[3].y - o[3].x) * H, (-o[3].x - o[3].y) * H);
+    v[0] = cadd(e[0], o[0]);
+    v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);
+    v[5] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);
+    v[6] = csub(e[2], o2);
+    v[3] = cadd(e[3], o3);
+    v[7] = csub(e[3], o3);
+  }
+};
+
+// ---------------------------------------------------------------- plans
+// A plan factorises N into up to five radices (1 = unused).  Stage s works in place on
+// sub-transforms of size sub(s) = N / (R0..R(s-1)); after the last stage, position p holds
+// the natural output index nat(p) (mixed-radix digit reversal).
+template <int R0, int R1 = 1, int R2 = 1, int R3 = 1, int R4 = 1>
+struct PlanT {
+  static constexpr int S = (R0 > 1) + (R1 > 1) + (R2 > 1) + (R3 > 1) + (R4 > 1);
+  static constexpr int N = R0 * R1 * R2 * R3 * R4;
+  __host__ __device__ static constexpr int radix(int s) {
+    return s == 0 ? R0 : s == 1 ? R1 : s == 2 ? R2 : s == 3 ? R3 : R4;
+  }
+  __host__ __device__ static constexpr int sub(int s) {
+    int m = N;
+    for (int i = 0; i < s; ++i) m /= radix(i);
+    return m;
+  }
+  // natural output index of in-place position p
+  __host__ __device__ static constexpr int nat(int p) {
+    int k = 0, w = 1;
+    for (int s = 0; s < S; ++s) {
+      int m = sub(s) / radix(s);
+      int q = p / m;
+      p -= q * m;
+      k += q * w;
+      w *= radix(s);
+    }
+    return k;
+  }
+  // in-place position of natural index k
+  __host__ __device__ static constexpr int pos(int k) {
+    int p = 0;
+    for (int s = 0; s < S; ++s) {
+      int q = k % radix(s);
+      k /= radix(s);
+      p += q * (sub(s) / radix(s));
+    }
+    return p;
+  }
+};
+
+template <int N>
+struct PlanFor;
+#define SMK_PLAN(N_, ...)          \
+  template <>                      \
+  struct PlanFor<N_> {             \
+    using type = PlanT<__VA_ARGS__>; \
+  };
+SMK_PLAN(4, 4)
+SMK_PLAN(8, 8)
+SMK_PLAN(12, 4, 3)
+SMK_PLAN(16, 4, 4)
+SMK_PLAN(24, 8, 3)
+SMK_PLAN(32, 8, 4)
+SMK_PLAN(48, 4, 4, 3)
+SMK_PLAN(64, 8, 8)
+SMK_PLAN(96, 8, 4, 3)
+SMK_PLAN(128, 8, 4, 4)
+SMK_PLAN(256, 8, 8, 4)
+SMK_PLAN(384, 8, 4, 4, 3)
+SMK_PLAN(512, 8, 8, 8)
+SMK_PLAN(768, 8, 8, 4, 3)
+SMK_PLAN(1024, 8, 8, 4, 4)
+SMK_PLAN(2048, 8, 8, 8, 4)
+SMK_PLAN(2560, 8, 8, 8, 5)
+SMK_PLAN(4096, 8, 8, 8, 8)
+#undef SMK_PLAN
+
+// ---------------------------------------------------------------- one DIF stage
+// Tile element (line, pos) is accessed through the functors:
+//   ld(line, pos)        -> float2     (input position, pre-stage)
+//   st(line, idx, value)
+// OUT selects what the store functor receives as idx and when it runs:
+//   OUT_INPLACE   idx = the in-place position (same set the task read);
+//   OUT_NATURAL   last stage only: idx = natural output index (stage writes elsewhere,
+//                 e.g. straight to global memory);
+//   OUT_RESORT    last stage only: idx = natural output index in the SAME buffer, so a
+//                 __syncthreads() separates all reads of the stage from all writes.
+// tw is the table W_L, L = N * twmul.
+enum { OUT_INPLACE = 0, OUT_NATURAL = 1, OUT_RESORT = 2 };
+
+template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store>
+__device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __restrict__ tw, int twmul) {
+  constexpr int R = P::radix(STAGE);
+  constexpr int M = P::sub(STAGE);
+  constexpr int MQ = M / R;
+  constexpr int NB = P::N / R;
+  constexpr int NTASK = NB * LINES;
+  constexpr bool LAST = (STAGE == P::S - 1);
+  static_assert(OUT == OUT_INPLACE || LAST, "natural-order store only on the last stage");
+  constexpr int TPT = (NTASK + NT - 1) / NT;
+  constexpr bool EVEN = (NTASK % NT == 0);
+  // phase 1: all loads of this thread (keeps TPT*R independent loads in flight)
+  float2 v[TPT][R];
+#pragma unroll
+  for (int i = 0; i < TPT; ++i) {
+    int task = threadIdx.x + i * NT;
+    if (EVEN || task < NTASK) {
+      int line = task % LINES, j = task / LINES;
+      int b = j / MQ, o = j - b * MQ;
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[i][t] = ld(line, b * M + o + t * MQ);
+    }
+  }
+  if (OUT == OUT_RESORT) __syncthreads();
+#pragma unroll
+  for (int i = 0; i < TPT; ++i) {
+    int task = threadIdx.x + i * NT;
+    if (EVEN || task < NTASK) {
+      int line = task % LINES, j = task / LINES;
+      int b = j / MQ, o = j - b * MQ;
+      Butterfly<R, INV>::run(v[i]);
+      if (!LAST) {
+#pragma unroll
+        for (int q = 1; q < R; ++q) {
+          float2 w = __ldg(tw + (o * q * (P::N / M)) * twmul);
+          if (INV) w.y = -w.y;
+          v[i][q] = cmul(v[i][q], w);
+        }
+      }
+      if (OUT != OUT_INPLACE) {
+        int nb = P::nat(b * M);
+#pragma unroll
+        for (int q = 0; q < R; ++q) st(line, nb + q * (P::N / R), v[i][q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < R; ++q) st(line, b * M + o + q * MQ, v[i][q]);
+      }
+    }
+  }
+}
+
+// Stages [S0, S1) in place in shared memory; element (line,pos) at sm[line*LS + pos*PS].
+// A __syncthreads() follows every stage.
+template <class P, int S0, int S1, bool INV, int LINES, int LS, int PS, int NT>
+__device__ __forceinline__ void dif_stages_smem(float2* sm, const float2* __restrict__ tw, int twmul) {
+  if constexpr (S0 < S1) {
+    auto ld = [&](int line, int pos) { return sm[line * LS + pos * PS]; };
+    auto st = [&](int line, int pos, float2 val) { sm[line * LS + pos * PS] = val; };
+    dif_stage<P, S0, INV, LINES, NT, OUT_INPLACE>(ld, st, tw, twmul);
+    __syncthreads();
+    dif_stages_smem<P, S0 + 1, S1, INV, LINES, LS, PS, NT>(sm, tw, twmul);
+  }
+}
+
+// Last stage with the outputs re-sorted to natural order inside the same buffer.
+template <class P, bool INV, int LINES, int LS, int PS, int NT>
+__device__ __forceinline__ void dif_last_resort_smem(float2* sm, const float2* __restrict__ tw, int twmul) {
+  auto ld = [&](int line, int pos) { return sm[line * LS + pos * PS]; };
+  auto st = [&](int line, int k, float2 val) { sm[line * LS + k * PS] = val; };
+  dif_stage<P, P::S - 1, INV, LINES, NT, OUT_RESORT>(ld, st, tw, twmul);
+  __syncthreads();
+}
+
+}  // namespace smk

@@ -1,0 +1,71 @@
+// Internal (C++) declarations shared by the translation units of libsmk.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/smk.h"
+
+namespace smk {
+
+void set_error(const std::string& msg);
+
+#define SMK_CUDA_OK(expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      smk::set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+      return SMK_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+// Addressing of one strided complex pass.  A tile is LINES consecutive z-columns (col0..)
+// of one `outer` index; point n of the transform sits at
+//   base + outer*outer_stride + (n / nsplit)*hi_stride + (n % nsplit)*lo_stride + col
+// (nsplit == N gives a plain stride; the two-level form addresses the [src][xl][yl][z]
+// layout that an all-to-all leaves behind without an unpack pass).
+struct PassAddr {
+  long long outer_stride;
+  long long hi_stride;
+  long long lo_stride;
+  int nsplit;
+};
+
+struct MulArgs {
+  // spectral weight table W[n][outer][col] (float) with its own strides, or null
+  const float* wt;
+  long long wt_n_stride;
+  long long wt_outer_stride;
+  // optional store-back of (in * W) to this array (same addressing as the input)
+  float2* store_back;
+  // k tables for the k-factor products (float32, reference rounding): kn = k along the
+  // transformed axis, ko = k along the outer axis, kc = k along the column (z) axis
+  const float* kn;
+  const float* ko;
+  const float* kc;
+  int outer0;      // global index of outer==0 (multi-GPU y offset)
+  int fa, fb;      // axes of the factor: 0 = n axis (x), 1 = outer axis (y), 2 = column axis (z)
+  double vscale;   // H0 * dgrowth0 for the velocity products
+};
+
+enum MulMode { MUL_NONE = 0, MUL_TABLE = 1, MUL_ETA = 2, MUL_VEL = 3 };
+
+int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, float2* out, PassAddr ain, PassAddr aout,
+                       int nouter, int ncols, const MulArgs& mul, const float2* tw, cudaStream_t st);
+
+int launch_r2c_z(int NZ, const float* in, float2* out, long long nlines, int pitch, const float2* tw,
+                 bool philox, uint64_t seed, long long cell0, cudaStream_t st);
+
+int launch_c2r_z(int NZ, const float2* in, float* out, long long nlines, int pitch, const float2* tw, float norm,
+                 double* stats, cudaStream_t st);
+
+int launch_philox_fill(float* out, long long ncells, uint64_t seed, long long cell0, cudaStream_t st);
+
+bool strided_size_supported(int n);
+bool z_size_supported(int nz);
+
+}  // namespace smk
+
+// stream of a context (defined in smk_capi.cu; smk_ctx is opaque to the other translation units)
+cudaStream_t smk_ctx_stream(const smk_ctx* ctx);

@@ -1,0 +1,196 @@
+"""Host side of the skewer stage: batched replacement of the per-quasar loop of bin/make_spectra.py:412-522
+and of the per-forest arithmetic of bin/merge_spectra.py:282-339, on top of libsmk.so."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import constant
+from . import cosmo as cosmo_mod
+from . import tables
+from .p1dmiss import InterpP1Dmissing
+
+FIELDS = ("box", "eta_xx", "eta_yy", "eta_zz", "eta_xy", "eta_xz", "eta_yz", "vx", "vy", "vz")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class SkewerGeometry(object):
+    """Box placement and the global pixel grid (make_spectra.py:196-206, 300-321)."""
+
+    def __init__(self, NX, NY, NZ, dcell, zmin=1.8, zmax=3.6, pixel=0.2, dmax=3):
+        self.NX, self.NY, self.NZ = int(NX), int(NY), int(NZ)
+        self.DX = self.DY = self.DZ = float(dcell)
+        self.LX, self.LY, self.LZ = self.DX * NX, self.DY * NY, self.DZ * NZ
+        self.dmax, self.pixel, self.zmin, self.zmax = int(dmax), float(pixel), float(zmin), float(zmax)
+        h = constant.h
+        self.cosmo = cosmo_mod.cosmo(constant.omega_M_0, Ok=constant.omega_k_0, H0=100 * h)
+        self.R0 = h * float(self.cosmo.r_comoving(constant.z0))
+        Rmin = h * float(self.cosmo.r_comoving(zmin))
+        Rmax = h * float(self.cosmo.r_comoving(zmax))
+        npixeltot = int((Rmax - Rmin) / pixel + 0.5)
+        R_vec = Rmin + np.arange(npixeltot) * pixel
+        lambda_vec = constant.lya * (1 + self.cosmo.r_2_z(R_vec / h))
+        cut = lambda_vec > constant.lambda_min
+        self.R_vec, self.lambda_vec = R_vec[cut], lambda_vec[cut]
+        self.redshift = self.cosmo.r_2_z(self.R_vec / h)          # per-pixel z, common to all quasars
+        self.npixeltot = len(self.R_vec)
+        z, dd, om = tables.dgrowth()
+        if om != constant.omega_M_0:                                # make_spectra.py:175-179
+            raise ValueError("Omega_M_0 in constant ({}) != OM in dgrowth table ({})".format(constant.omega_M_0, om))
+        self._dg = (z, dd)
+        self.dgrowth0 = float(cosmo_mod.lin_interp(z, dd, 0.0))
+
+    def velo_rescale(self):
+        """(1+z) D_H(z)/D_H(0) D'(z)/D'(0) per pixel (make_spectra.py:510)."""
+        z = self.redshift
+        return ((1 + z) * self.cosmo.dist_hubble(z) / self.cosmo.dist_hubble(0.)
+                * cosmo_mod.lin_interp(self._dg[0], self._dg[1], z) / self.dgrowth0)
+
+    def c_geom(self):
+        return _lib.Geom(self.NX, self.NY, self.NZ, self.DX, self.DY, self.DZ, self.R0, self.dmax)
+
+
+def qso_lines_of_sight(geom, ra, dec, zqso, ra0, dec0):
+    """Vectorised make_spectra.py:429-431, 467-472: per-quasar (X,Y,Z,R_QSO) and forest length on the global grid.
+    Quasars outside [zmin, zmax] (make_spectra.py:437-438) get a forest length of -1 (caller drops them)."""
+    h = constant.h
+    zq = np.asarray(zqso, dtype=np.float64)
+    ok = (zq >= geom.zmin) & (zq <= geom.zmax)
+    R = h * geom.cosmo.r_comoving(np.where(ok, zq, geom.zmin))
+    X, Y, Z = cosmo_mod.ComputeXYZ2(np.radians(np.asarray(ra, dtype=np.float64)),
+                                    np.radians(np.asarray(dec, dtype=np.float64)), R, np.radians(ra0), np.radians(dec0))
+    nfor = np.searchsorted(geom.lambda_vec, constant.lya * (1 + zq), side="left").astype(np.int32)
+    nfor[~ok] = -1
+    return np.stack([X, Y, Z, R], axis=1), nfor
+
+
+class SkewerEngine(object):
+    def __init__(self, geom, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.SmkError("SkewerEngine needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.lib()
+        self.geom = geom
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.rvec = torch.as_tensor(geom.R_vec, dtype=torch.float64, device=self.device)
+
+    def read_spec(self, fields, xyzr, nforest, ix0=0, xmin=None, xmax=None, rsd=True, dla=True, out=None):
+        """Batched ReadSpec over one slab.  fields: dict name -> device float32 [nxs, NY, NZ].
+        Returns (delta_l, eta_par, vpar) device tensors [nqso, npix]; pixels not owned by the slab keep the
+        initial NaN (so that merging slabs is a select)."""
+        g = self.geom
+        nq = len(nforest)
+        npix = g.npixeltot
+        xmin = -g.LX / 2 if xmin is None else xmin
+        xmax = g.LX / 2 if xmax is None else xmax
+        fl = (C.c_void_p * 10)()
+        nxs = None
+        for i, k in enumerate(FIELDS):
+            t = fields.get(k)
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                nxs = t.shape[0]
+                fl[i] = t.data_ptr()
+        if out is None:
+            out = tuple(torch.full((nq, npix), float("nan"), dtype=torch.float32, device=self.device) for _ in range(3))
+        q = torch.as_tensor(np.ascontiguousarray(xyzr, dtype=np.float64), device=self.device)
+        nf = torch.as_tensor(np.ascontiguousarray(nforest, dtype=np.int32), device=self.device)
+        cg = g.c_geom()
+        _lib.check(self.lib.smk_skewers(None, C.byref(cg), fl, int(ix0), int(nxs), C.c_double(xmin), C.c_double(xmax),
+                                        int(rsd), int(dla), nq, _ptr(q), _ptr(nf), _ptr(self.rvec), npix,
+                                        _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return out
+
+
+class FGPA(object):
+    """Small-scale field + FGPA for complete forests (merge_spectra.py:285-339)."""
+
+    def __init__(self, geom, zfix=None, aa=-1, bb=-1, cc=-1, pixsize=0.2, p1dfile=None, paramfile=None, device=None):
+        self.lib = _lib.lib()
+        self.geom = geom
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.pixsize = pixsize
+        z = np.full(geom.npixeltot, zfix, dtype=np.float64) if zfix else geom.redshift.copy()
+        self.z = z
+        pz, pa, pb, pc = tables.params(paramfile)
+        a = cosmo_mod.lin_interp(pz, pa, z) if aa <= 0 else np.full_like(z, aa)
+        b = cosmo_mod.lin_interp(pz, pb, z) if bb <= 0 else np.full_like(z, bb)
+        c = cosmo_mod.lin_interp(pz, pc, z) if cc <= 0 else np.full_like(z, cc)
+        growthf = cosmo_mod.fgrowth(2.4, constant.omega_M_0) * (1 + 2.4) / (1 + z)     # merge_spectra.py:296
+        self.growthf = growthf
+        f32 = lambda v: torch.as_tensor(np.float32(v), device=self.device)
+        self.a, self.b, self.c, self.G = f32(a), f32(b), f32(c), f32(growthf)
+        self.p1d = InterpP1Dmissing(p1dfile)
+        self.sig_pix_np = cosmo_mod.lin_interp(self.p1d.z, self.p1d.sigma, z)          # sigma_s(z) per pixel
+        self.sig_pix = f32(self.sig_pix_np)
+        self._filt = {}
+
+    def nfft_for(self, n):
+        nz = 256
+        while nz < n + 50:                       # merge_spectra.py:308-309
+            nz *= 2
+        return nz
+
+    def filt_rows(self, nfft):
+        """sqrt(max(P_miss(z_row, k), 0) / pixsize) for every tabulated z (merge_spectra.py:312-320)."""
+        if nfft not in self._filt:
+            k = np.fft.rfftfreq(nfft) * 2 * np.pi / self.pixsize
+            rows = []
+            for iz in range(len(self.p1d.z)):
+                pm = np.interp(k, self.p1d.k, self.p1d.pk[iz])
+                pm[pm < 0] = 0
+                rows.append(np.sqrt(pm / self.pixsize))
+            self._filt[nfft] = torch.as_tensor(np.float32(rows), device=self.device)
+        return self._filt[nfft]
+
+    def forest_count(self, zqso):
+        """Number of pixels merge_spectra counts as forest (merge_spectra.py:305-306): float32 LAMBDA divided by
+        float32 (1+z) compared with lya in float32.  The mask is a prefix of the wavelength-sorted row."""
+        lam32 = np.float32(self.geom.lambda_vec)
+        z32 = np.asarray(zqso, dtype=np.float32)
+        one_plus = (np.float32(1) + z32).astype(np.float32)
+        n0 = np.searchsorted(self.geom.lambda_vec, constant.lya * (1 + z32.astype(np.float64)))
+        npix = len(lam32)
+        cnt = np.zeros(len(z32), dtype=np.int64)
+        for j in range(-3, 4):
+            idx = n0 + j
+            ok = (idx >= 0) & (idx < npix)
+            v = lam32[np.clip(idx, 0, npix - 1)] / one_plus
+            cnt += (ok & (v < np.float32(constant.lya)) & (v > np.float32(constant.lylimit))) | (ok & (j < 0) & False)
+        return np.clip(n0 - 3, 0, npix) + cnt
+
+    def zeff(self, nforest):
+        """Mean z over the forest pixels of each quasar (merge_spectra.py:313); forest = first nforest pixels."""
+        cs = np.concatenate(([0.], np.cumsum(self.z)))
+        n = np.maximum(np.asarray(nforest), 1)
+        return cs[n] / n
+
+    def small_scales(self, nforest, noise=None, seed=0):
+        """delta_s [nqso, npix] (zero rows for quasars with an empty forest, merge_spectra.py:327-330)."""
+        nq, npix = len(nforest), self.geom.npixeltot
+        nfft = self.nfft_for(npix)
+        zeff = self.zeff(nforest)
+        rows = np.array([self.p1d.iz(z) for z in zeff], dtype=np.int32)
+        sig_eff = np.float32(cosmo_mod.lin_interp(self.p1d.z, self.p1d.sigma, zeff))
+        d = torch.empty((nq, npix), dtype=torch.float32, device=self.device)
+        nz_t = None
+        if noise is not None:
+            nz_t = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32), device=self.device)
+            assert tuple(nz_t.shape) == (nq, nfft)
+        _lib.check(self.lib.smk_smallscale(None, nq, nfft, npix, _ptr(nz_t), C.c_uint64(seed), _ptr(self.filt_rows(nfft)),
+                                           _ptr(torch.as_tensor(rows, device=self.device)), _ptr(self.sig_pix),
+                                           _ptr(torch.as_tensor(sig_eff, device=self.device)), _ptr(d)))
+        empty = torch.as_tensor(np.asarray(nforest) <= 0, device=self.device)
+        if bool(empty.any()):
+            d[empty] = 0
+        return d
+
+    def flux(self, delta_l, delta_s=None, eta_par=None):
+        nq, npix = delta_l.shape
+        F = torch.empty_like(delta_l)
+        _lib.check(self.lib.smk_fgpa(None, nq, npix, _ptr(delta_l), _ptr(delta_s), _ptr(eta_par), _ptr(self.G),
+                                     _ptr(self.a), _ptr(self.b), _ptr(self.c), _ptr(F)))
+        return F
