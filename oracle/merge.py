@@ -94,6 +94,7 @@ def merge_spectra_hdu(pieces, islice, seed, p1d, npixeltot, zfix=None, rsd=True,
             vpar = np.concatenate([p["velo_par"] for p in sel])[order]
             delta_s = np.zeros_like(delta_l)
             delta = delta_l
+            noise = None
             if add_noise:
                 wav_rf = wav / (1 + ZQ[msk][0])
                 mmm = np.where((wav_rf < co.lya) & (wav_rf > co.lylimit))[0]
@@ -114,7 +115,7 @@ def merge_spectra_hdu(pieces, islice, seed, p1d, npixeltot, zfix=None, rsd=True,
                 continue
             out.append(dict(id=int(ID), pix=int(pix), flux=np.float32(spec), delta_l=np.float32(delta_l),
                             eta_par=np.float32(eta), velo_par=np.float32(vpar), delta_s=np.float32(delta_s),
-                            lam=np.float32(wav), z=np.float32(z), growthf=np.float32(growthf)))
+                            lam=np.float32(wav), z=np.float32(z), growthf=np.float32(growthf), noise=noise))
     if return_noise:
         return out, noises
     return out

@@ -48,7 +48,10 @@ class cosmo(object):
 
 def ComputeXYZ2(ra, dec, R, ra0, dec0):
     """(ra, dec, R) -> box frame, angles in radians (box.py:240-250)."""
-    cd, sd, cr, sr = np.cos(dec), np.sin(dec), np.cos(ra), np.sin(ra)
+    # cos/sin run in the dtype of ra/dec (float32 for catalogue columns, as in the reference) and are then
+    # promoted to float64 by the float64 factors
+    f64 = np.float64
+    cd, sd, cr, sr = f64(np.cos(dec)), f64(np.sin(dec)), f64(np.cos(ra)), f64(np.sin(ra))
     c0, s0, cr0, sr0 = np.cos(dec0), np.sin(dec0), np.cos(ra0), np.sin(ra0)
     x = R * (cr0 * cd * sr - sr0 * cd * cr)
     y = R * (-sr0 * s0 * cd * sr + c0 * sd - cr0 * s0 * cd * cr)

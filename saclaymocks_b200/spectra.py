@@ -61,8 +61,12 @@ def qso_lines_of_sight(geom, ra, dec, zqso, ra0, dec0):
     zq = np.asarray(zqso, dtype=np.float64)
     ok = (zq >= geom.zmin) & (zq <= geom.zmax)
     R = h * geom.cosmo.r_comoving(np.where(ok, zq, geom.zmin))
-    X, Y, Z = cosmo_mod.ComputeXYZ2(np.radians(np.asarray(ra, dtype=np.float64)),
-                                    np.radians(np.asarray(dec, dtype=np.float64)), R, np.radians(ra0), np.radians(dec0))
+    # The catalogue stores RA/DEC as float32 and the reference takes np.radians / cos / sin of those float32
+    # scalars (make_spectra.py:414-431), i.e. float32 trigonometry promoted to float64 in the products.  Keep that:
+    # float64 trigonometry moves a pixel by ~4e-4 Mpc/h, which is visible (1e-4) in delta_l at 2.19 Mpc/h cells.
+    ra32 = np.radians(np.asarray(ra, dtype=np.float32))
+    dec32 = np.radians(np.asarray(dec, dtype=np.float32))
+    X, Y, Z = cosmo_mod.ComputeXYZ2(ra32, dec32, R, np.radians(ra0), np.radians(dec0))
     nfor = np.searchsorted(geom.lambda_vec, constant.lya * (1 + zq), side="left").astype(np.int32)
     nfor[~ok] = -1
     return np.stack([X, Y, Z, R], axis=1), nfor
@@ -163,10 +167,14 @@ class FGPA(object):
         return np.clip(n0 - 3, 0, npix) + cnt
 
     def zeff(self, nforest):
-        """Mean z over the forest pixels of each quasar (merge_spectra.py:313); forest = first nforest pixels."""
-        cs = np.concatenate(([0.], np.cumsum(self.z)))
-        n = np.maximum(np.asarray(nforest), 1)
-        return cs[n] / n
+        """z[mmm].mean() of merge_spectra.py:313 (forest = first nforest pixels of the row).  np.mean's pairwise
+        summation is kept on purpose: with -zfix 2.4 the nearest tabulated P1D_miss redshift is a tie between 2.2
+        and 2.6 that is decided by the last bit of this mean, so the exact reduction order matters for parity.
+        At most npix distinct prefix lengths exist, so this is one small reduction per distinct length."""
+        n = np.maximum(np.asarray(nforest, dtype=np.int64), 1)
+        uniq, inv = np.unique(n, return_inverse=True)
+        means = np.array([self.z[:k].mean() for k in uniq])
+        return means[inv]
 
     def small_scales(self, nforest, noise=None, seed=0):
         """delta_s [nqso, npix] (zero rows for quasars with an empty forest, merge_spectra.py:327-330)."""
@@ -180,9 +188,10 @@ class FGPA(object):
         if noise is not None:
             nz_t = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32), device=self.device)
             assert tuple(nz_t.shape) == (nq, nfft)
+        rows_t = torch.as_tensor(rows, device=self.device)          # keep alive across the call
+        sig_eff_t = torch.as_tensor(sig_eff, device=self.device)
         _lib.check(self.lib.smk_smallscale(None, nq, nfft, npix, _ptr(nz_t), C.c_uint64(seed), _ptr(self.filt_rows(nfft)),
-                                           _ptr(torch.as_tensor(rows, device=self.device)), _ptr(self.sig_pix),
-                                           _ptr(torch.as_tensor(sig_eff, device=self.device)), _ptr(d)))
+                                           _ptr(rows_t), _ptr(self.sig_pix), _ptr(sig_eff_t), _ptr(d)))
         empty = torch.as_tensor(np.asarray(nforest) <= 0, device=self.device)
         if bool(empty.any()):
             d[empty] = 0

@@ -1,0 +1,194 @@
+"""GPU parity of the skewer stage (gather, small-scale field, FGPA) against the oracle and the reference goldens.
+Tolerances (BASELINE.json north_star): transmissions within 1e-5 absolute."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from helpers import qso_files_from_golden  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _gpu_skewers(g, boxes, cuda, rsd=True, dla=True, slabs=1):
+    from saclaymocks_b200 import spectra as sp
+    NX, NY, NZ, dcell = int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"])
+    geom = sp.SkewerGeometry(NX, NY, NZ, dcell)
+    q = np.concatenate(qso_files_from_golden(g))
+    zq = q["Z_QSO_RSD"] if rsd else q["Z_QSO_NO_RSD"]
+    xyzr, nfor = sp.qso_lines_of_sight(geom, q["RA"], q["DEC"], zq, float(g["ra0"]), float(g["dec0"]))
+    eng = sp.SkewerEngine(geom, device=cuda)
+    out = None
+    for s in range(slabs):          # x-slab decomposition with dmax halo planes, like make_spectra -i s -N slabs
+        lo, hi = max(s * NX // slabs - geom.dmax, 0), min((s + 1) * NX // slabs + geom.dmax, NX)
+        f = {k: torch.as_tensor(np.ascontiguousarray(boxes[k][lo:hi]), device=cuda) for k in sp.FIELDS}
+        xmin, xmax = geom.LX * s / slabs - geom.LX / 2, geom.LX * (s + 1) / slabs - geom.LX / 2
+        out = eng.read_spec(f, xyzr, np.maximum(nfor, 0), ix0=lo, xmin=xmin, xmax=xmax, rsd=rsd, dla=dla, out=out)
+    return geom, q, xyzr, nfor, out
+
+
+def _compare_with_pieces(g, geom, q, out):
+    """Golden make_spectra pieces (per slab) against the full-row GPU result, matched by wavelength."""
+    d, e, v = (t.cpu().numpy() for t in out)
+    v = v * np.float32(1) * geom.velo_rescale()[None, :]            # make_spectra.py:510
+    lam32 = np.float32(geom.lambda_vec)
+    ids = list(q["THING_ID"])
+    n = 0
+    for key in [k[:-len("_THING_ID")] for k in g if k.startswith("spectra_") and k.endswith("_THING_ID")]:
+        for r, ID in enumerate(g[key + "_THING_ID"]):
+            lam = g[key + "_LAMBDA"][r]
+            m = lam > 0
+            idx = np.searchsorted(lam32, lam[m])
+            assert np.array_equal(lam32[idx], lam[m])
+            row = ids.index(ID)
+            for ext, arr, tol in (("DELTA_L", d, 5e-6), ("ETA_PAR", e, 5e-6), ("VELO_PAR", v, 2e-3)):
+                ref = g[key + "_" + ext][r][m]
+                assert np.max(np.abs(arr[row, idx] - ref)) < tol * max(1.0, np.abs(ref[ref > -1e5]).max()
+                                                                      if np.any(ref > -1e5) else 1.0), (key, ID, ext)
+            n += 1
+    assert n > 0
+
+
+def test_skewers_match_reference_small(cuda, golden_small):
+    g = golden_small
+    from saclaymocks_b200 import spectra as sp
+    boxes = {k: g["box_" + k] for k in sp.FIELDS}
+    geom, q, xyzr, nfor, out = _gpu_skewers(g, boxes, cuda)
+    _compare_with_pieces(g, geom, q, out)
+
+
+def test_skewers_slab_decomposition_is_exact(cuda, golden_small):
+    """Sharding by the slab that owns the pixel (make_spectra.py:443-448) gives bit-identical rows."""
+    g = golden_small
+    from saclaymocks_b200 import spectra as sp
+    boxes = {k: g["box_" + k] for k in sp.FIELDS}
+    _, _, _, _, full = _gpu_skewers(g, boxes, cuda, slabs=1)
+    _, _, _, _, slab = _gpu_skewers(g, boxes, cuda, slabs=4)
+    for a, b in zip(full, slab):
+        assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+
+
+def test_skewers_vs_oracle_no_dla_no_rsd(cuda, golden_small):
+    from oracle import spectra as osp
+    from saclaymocks_b200 import spectra as sp
+    g = golden_small
+    boxes = {k: g["box_" + k] for k in sp.FIELDS}
+    for rsd, dla in ((True, False), (False, False)):
+        geom, q, xyzr, nfor, out = _gpu_skewers(g, boxes, cuda, rsd=rsd, dla=dla)
+        og = osp.Geometry(int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"]))
+        qf = qso_files_from_golden(g)
+        ns = int(g["nslice"])
+        d = out[0].cpu().numpy()
+        e = out[1].cpu().numpy()
+        ids = list(q["THING_ID"])
+        lam32 = np.float32(geom.lambda_vec)
+        for s in range(ns):
+            for p in osp.make_spectra_slice(og, boxes, qf, s, ns, float(g["ra0"]), float(g["dec0"]), rsd=rsd, dla=dla):
+                idx = np.searchsorted(lam32, p["lam"])
+                row = ids.index(p["id"])
+                assert np.max(np.abs(d[row, idx] - p["delta_l"])) < 5e-6 * 1e0 or np.all(p["delta_l"] < -1e5)
+                assert np.max(np.abs(e[row, idx] - p["eta_par"])) < 5e-6
+
+
+def test_end_to_end_ref32(cuda, golden_ref32):
+    """32 x 32 x 1536 reference run: MT19937 noise -> GPU boxes -> GPU skewers -> GPU delta_s (reference noise
+    stream) + FGPA -> FLUX of the unmodified merge_spectra.py within 1e-5 absolute."""
+    from oracle import boxes as ob
+    from oracle import pk_weights
+    from oracle import merge as om
+    from saclaymocks_b200 import spectra as sp
+    from saclaymocks_b200.boxes import BoxSynth, WEIGHT_OF
+    g = golden_ref32
+    NX, NY, NZ, dcell = int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"])
+    W = pk_weights.weights(NX, NY, NZ, dcell)
+    noise = ob.draw_noise(NX, NY, NZ, int(g["seed"]))
+    bs = BoxSynth(NX, NY, NZ, dcell, device=cuda)
+    boxk = bs.draw_grf_boxk(noise=torch.as_tensor(noise, device=cuda))
+    Wd = {k: bs.upload_weights(v) for k, v in W.items()}
+    bs.synth(boxk, "box", wtable=Wd["P0"])[0]
+    fields = {}
+    for name in sp.FIELDS:
+        fields[name] = bs.synth(boxk, name, wtable=Wd.get(WEIGHT_OF.get(name)), store_p0=False)[0] \
+            if name != "box" else None
+    # 'box' must be synthesised from the raw boxk: redo the chain in reference order
+    boxk = bs.draw_grf_boxk(noise=torch.as_tensor(noise, device=cuda))
+    fields["box"] = bs.synth(boxk, "box", wtable=Wd["P0"])[0]
+    for name in sp.FIELDS[1:]:
+        fields[name] = bs.synth(boxk, name)[0]
+    st = int(g["stride"])
+    for name in sp.FIELDS:
+        ref = g["box_" + name]
+        got = fields[name].cpu().numpy().ravel()[::st]
+        assert np.sqrt(((got - ref) ** 2).sum() / (ref ** 2).sum()) < 1e-5, name
+    geom = sp.SkewerGeometry(NX, NY, NZ, dcell)
+    q = np.concatenate(qso_files_from_golden(g))
+    xyzr, nfor = sp.qso_lines_of_sight(geom, q["RA"], q["DEC"], q["Z_QSO_RSD"], float(g["ra0"]), float(g["dec0"]))
+    eng = sp.SkewerEngine(geom, device=cuda)
+    out = eng.read_spec(fields, xyzr, np.maximum(nfor, 0))
+    _compare_with_pieces(g, geom, q, out)
+    # merge stage: the oracle's bookkeeping (pinned against merge_spectra.py on CPU) replays the reference's
+    # np.random stream per HDU and hands back the white noise each written forest consumed; delta_s and FGPA
+    # then run on the GPU from the GPU skewers.
+    ids = list(q["THING_ID"])
+    pieces = []
+    for key in [k[:-len("_THING_ID")] for k in g if k.startswith("spectra_") and k.endswith("_THING_ID")]:
+        for r, ID in enumerate(g[key + "_THING_ID"]):
+            m = g[key + "_LAMBDA"][r] > 0
+            row = ids.index(ID)
+            pieces.append(dict(id=int(ID), hdu=int(q["HDU"][row]), ra=q["RA"][row], dec=q["DEC"][row],
+                               z=q["Z_QSO_RSD"][row], lam=g[key + "_LAMBDA"][r][m], delta_l=g[key + "_DELTA_L"][r][m],
+                               eta_par=g[key + "_ETA_PAR"][r][m], velo_par=g[key + "_VELO_PAR"][r][m],
+                               redshift=g[key + "_REDSHIFT"][r][m]))
+    p1d = om.P1DMissing()
+    for mode, zfix in (("merged_zfix", 2.4), ("merged_z", None)):
+        fg = sp.FGPA(geom, zfix=zfix, device=cuda)
+        merged = []
+        for hdu in range(int(g["nslice"])):
+            sel = [p for p in pieces if p["hdu"] == hdu]
+            if sel:
+                merged += om.merge_spectra_hdu(sel, hdu, int(g["seed"]), p1d, geom.npixeltot, zfix=zfix)
+        by_id = {m["id"]: m for m in merged}
+        ref_ids = list(g[mode + "_THING_ID"])
+        rows = np.array([ids.index(i) for i in ref_ids])
+        noise = np.array([by_id[i]["noise"] for i in ref_ids])
+        nf_merge = fg.forest_count(q["Z_QSO_RSD"][rows])
+        ds = fg.small_scales(nf_merge, noise=noise)
+        F = fg.flux(out[0][rows].contiguous(), ds, out[1][rows].contiguous()).cpu().numpy()
+        assert np.max(np.abs(ds.cpu().numpy() - g[mode + "_DELTA_S"])) < 1e-5
+        assert np.max(np.abs(F - g[mode + "_FLUX"])) < 1e-5
+    bs.close()
+
+
+def test_smallscale_and_fgpa_vs_oracle(cuda):
+    from oracle import merge as om
+    from saclaymocks_b200 import spectra as sp
+    geom = sp.SkewerGeometry(32, 32, 1536, 2.19)
+    rng = np.random.default_rng(5)
+    nq = 7
+    zq = rng.uniform(2.0, 3.5, nq)
+    for zfix in (2.4, None):
+        fg = sp.FGPA(geom, zfix=zfix, device=cuda)
+        nf = fg.forest_count(zq)
+        noise = rng.normal(size=(nq, 8192))
+        ds = fg.small_scales(nf, noise=noise).cpu().numpy()
+        p1d = om.P1DMissing()
+        z = fg.z
+        for i in range(nq):
+            zeff = z[:nf[i]].mean()
+            ref = om.small_scale_field(noise[i], geom.npixeltot, zeff, z, p1d)
+            assert np.max(np.abs(ds[i] - ref)) < 2e-5      # |delta_s| reaches ~10: 2e-6 relative
+        dl = rng.normal(0, 1.2, (nq, geom.npixeltot)).astype(np.float32)
+        dl[:, -100:] = -1e6
+        eta = rng.normal(0, 0.5, (nq, geom.npixeltot)).astype(np.float32)
+        F = fg.flux(torch.as_tensor(dl, device=cuda), torch.as_tensor(ds, device=cuda),
+                    torch.as_tensor(eta, device=cuda)).cpu().numpy()
+        ref = om.fgpa(dl.astype(np.float64) + ds, eta.astype(np.float64), fg.growthf, fg.a.cpu().numpy().astype(np.float64),
+                      fg.b.cpu().numpy().astype(np.float64), fg.c.cpu().numpy().astype(np.float64))
+        assert np.max(np.abs(F - ref)) < 1e-5
+        assert np.all(F[:, -100:] == 1.0)
