@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one "step" = one chunk = Philox noise + r2c + 13 x (weight/k-factor + c2r + sigma)
++ full-density skewers (gather + small-scale field + FGPA) on synthetic input of the BASELINE.json shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--box NX] [--impl reference]
+
+Prints ONE JSON line (see the driver contract in the task statement).  `value` = chunk cells / device time of the
+whole step with inputs resident in HBM; `e2e` = same through host buffers (pinned weights in, every box and
+every spectrum row copied back); `roofline` = the slowest FFT pass kernel against the measured HBM copy peak;
+`cpu_baseline` = the CPU oracle (restated reference, scipy.fft + numba) on a bounded sample on this host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNKS = {  # box size -> (ra0, dec0, half-width deg) of chunk 1, bin/submit_mocks.py:611-674
+    128: (190.0, 0.0, 1.6), 256: (189.982649735, 20.0, 3.17), 512: (190.0, 0.0, 6.4), 1024: (190.0, 0.0, 12.7),
+    2560: (125.5, 20.0, 32.2413248675)}
+QSO_DENSITY = 89.8          # per deg^2 for 1.8 < z < 3.6 from etc/nz_qso_desi.dat
+DCELL = 2.19
+NZ = 1536
+
+
+# ------------------------------------------------------------------------------------------------ synthetic input
+def synthetic_qsos(nx, ny, seed=42):
+    """Uniform in the chunk window, z from etc/nz_qso_desi.dat restricted to 1.8 < z < 3.6 (full density)."""
+    from saclaymocks_b200 import tables
+    ra0, dec0, half = CHUNKS.get(nx, (190.0, 0.0, 6.4 * nx / 512.0))
+    half_y = half * ny / nx
+    rng = np.random.default_rng(seed)
+    n = int(QSO_DENSITY * (2 * half) * (2 * half_y))
+    nz = tables.nz_qso_desi()
+    zc, w = 0.5 * (nz[:, 0] + nz[:, 1]), nz[:, 2].copy()
+    w[(zc < 1.8) | (zc > 3.6)] = 0
+    b = rng.choice(len(zc), size=n, p=w / w.sum())
+    z = np.clip(nz[b, 0] + rng.uniform(0, 1, n) * (nz[b, 1] - nz[b, 0]), 1.8001, 3.5999).astype(np.float32)
+    ra = (ra0 + rng.uniform(-half, half, n)).astype(np.float32)
+    dec = (dec0 + rng.uniform(-half_y, half_y, n)).astype(np.float32)
+    return ra, dec, z, ra0, dec0
+
+
+def weight_tables_device(bs, device):
+    """sqrt(P(|k|)/Vcell) for Pln1..3, P0 on this rank's k-slab, evaluated on the GPU from a fine 1-D table of the
+    oracle-independent spline.  Bench input preparation only (not timed, not the product path): parity runs use the
+    exact tables of interpolate_pk."""
+    import torch
+    from saclaymocks_b200 import pk
+    out = {}
+    k_ny = np.pi / bs.dcell
+    kx = torch.as_tensor(np.float32(np.fft.fftfreq(bs.NX) * 2 * k_ny), device=device)
+    ky = torch.as_tensor(np.float32(np.fft.fftfreq(bs.NY) * 2 * k_ny), device=device)
+    ky = ky[bs.rank * bs.nyl:(bs.rank + 1) * bs.nyl]
+    kz = torch.as_tensor(np.float32(np.fft.rfftfreq(bs.NZ) * 2 * k_ny), device=device)
+    kmax = float(np.sqrt(3.0) * k_ny * 1.001)
+    for name in ("Pln1", "Pln2", "Pln3", "P0"):
+        kk, ww = pk.weight_curve(name, bs.dcell, kmax, n=1 << 20)
+        tab = torch.as_tensor(np.float32(ww), device=device)
+        dk = float(kk[1] - kk[0])
+        W = torch.empty((bs.NX, bs.nyl, bs.nzh), dtype=torch.float32, device=device)
+        for i0 in range(0, bs.NX, 64):
+            k = torch.sqrt(kx[i0:i0 + 64, None, None] ** 2 + ky[None, :, None] ** 2 + kz[None, None, :] ** 2) / dk
+            j = k.floor().clamp_(0, len(ww) - 2).long()
+            f = k - j
+            W[i0:i0 + 64] = tab[j] * (1 - f) + tab[j + 1] * f
+        out[name] = W
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    def __init__(self, gpu_index=0):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self.idx = gpu_index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(o[0]))
+                self.max_mhz = float(o[1])
+                for nm, v in zip(names, o[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle timing
+def _skewer_worker(args):
+    (NX, NY, NZ_, dcell, seed, nq) = args
+    from oracle import spectra as osp
+    rng = np.random.default_rng(seed)
+    boxes = {k: rng.standard_normal((NX, NY, NZ_), dtype=np.float32) for k in osp.FIELDS}
+    geom = osp.Geometry(NX, NY, NZ_, dcell)
+    ra, dec, z, ra0, dec0 = synthetic_qsos(NX, NY, seed)
+    q = np.zeros(nq, dtype=[("RA", "f4"), ("DEC", "f4"), ("Z_QSO_NO_RSD", "f4"), ("Z_QSO_RSD", "f4"),
+                            ("THING_ID", "i8"), ("HDU", "i4")])
+    sel = rng.choice(len(ra), nq, replace=False)
+    q["RA"], q["DEC"], q["Z_QSO_RSD"], q["Z_QSO_NO_RSD"] = ra[sel], dec[sel], z[sel], z[sel]
+    osp.make_spectra_slice(geom, boxes, [q[:1]], 0, 1, ra0, dec0)          # numba warm-up, not timed
+    t0 = time.time()
+    pieces = osp.make_spectra_slice(geom, boxes, [q], 0, 1, ra0, dec0)
+    dt = time.time() - t0
+    return sum(p["npix_forest"] for p in pieces), dt
+
+
+def cpu_oracle_step(nx, workers, nq_per_worker=24, skewer_procs=None):
+    """One bounded sample of the chunk on the CPU oracle: a nx x nx x 1536 box through all 13 products plus skewers
+    at full density, the skewer time extrapolated from nq_per_worker quasars per core running on all cores."""
+    from multiprocessing import get_context
+    from oracle import boxes as ob
+    dcell = DCELL
+    t0 = time.time()
+    rng = np.random.default_rng(1)
+    W = {k: rng.random((nx, nx, NZ // 2 + 1), dtype=np.float32) for k in ("Pln1", "Pln2", "Pln3", "P0")}   # synthetic
+    t1 = time.time()
+    ob.make_boxes(nx, nx, NZ, dcell, 42, W, workers=workers)
+    t_boxes = time.time() - t1
+    procs = skewer_procs or workers
+    with get_context("fork").Pool(procs) as pool:
+        res = pool.map(_skewer_worker, [(32, 32, NZ, dcell, 100 + i, nq_per_worker) for i in range(procs)])
+    npx = sum(r[0] for r in res)
+    rate = sum(r[0] / r[1] for r in res)                 # aggregate pixels/s with `procs` processes
+    ra, dec, z, _, _ = synthetic_qsos(nx, nx)
+    from oracle import spectra as osp
+    geom = osp.Geometry(nx, nx, NZ, dcell)
+    npx_full = int(np.searchsorted(geom.lambda_vec, 1215.67 * (1 + z.astype(np.float64))).sum())
+    t_skew = npx_full / rate
+    cells = nx * nx * NZ
+    return {"cells": cells, "t_boxes": t_boxes, "t_skewers_extrapolated": t_skew, "skewer_pixels_per_s": rate,
+            "npix_sampled": npx, "npix_full": npx_full, "setup_s": t1 - t0,
+            "value": cells / (t_boxes + t_skew)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (restated as the oracle: the reference is
+    Python and its FFTW/fitsio/healpy wheels are absent) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    nx = 128
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.time()
+        r = cpu_oracle_step(nx, cores, nq_per_worker=8)
+        if i >= args.warmup:
+            vals.append(r["value"])
+            times.append(time.time() - t0)
+    v = float(np.mean(vals))
+    sample = ("%dx%dx1536 box, 13 products (scipy.fft float32, workers=%d) + numba ReadSpec on 8 quasars/core "
+              "extrapolated to the box's full-density catalogue; pocketfft stands in for FFTW" % (nx, nx, cores))
+    line = {"impl": "reference", "metric": "grf_cells_per_s", "value": v, "unit": "cells/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "chunk: noise + r2c + 13 products + full-density skewers/FGPA, bounded sample",
+                       "box": [nx, nx, NZ]},
+            "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from saclaymocks_b200 import spectra as sp
+    from saclaymocks_b200.chunk import ChunkPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # weak scaling: per-GPU work fixed at one 512 x 512 x 1536 chunk's worth of cells
+    if args.box:
+        nx = ny = args.box
+    else:
+        nx, ny = {1: (512, 512), 2: (1024, 512), 4: (1024, 1024), 8: (2048, 1024)}[world]
+    pipe = ChunkPipeline(nx, ny, NZ, DCELL, device=dev, rank=rank, nranks=world)
+    W = weight_tables_device(pipe.bs, dev)
+    ra, dec, z, ra0, dec0 = synthetic_qsos(nx, ny)
+    pipe.set_catalogue(ra, dec, z, ra0, dec0)
+    pipe.set_weights(W)
+    cells = nx * ny * NZ
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        pipe.step(seed=42)
+    barrier()
+    pipe.bs.timing_enable(True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    with ClockSampler(local) as clk:
+        barrier()
+        t0 = time.time()
+        for i in range(args.steps):
+            ev[3 * i].record()
+            pipe.step_boxes(seed=42 + i)
+            ev[3 * i + 1].record()
+            pipe.step_skewers(seed=42 + i)
+            ev[3 * i + 2].record()
+        ev[3 * args.steps].record()
+        barrier()
+        wall = time.time() - t0
+    passes = pipe.bs.timing_collect()
+    pipe.bs.timing_enable(False)
+    t_box = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
+    t_skw = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
+    t_tot = ev[0].elapsed_time(ev[3 * args.steps]) / args.steps
+    t = torch.tensor([t_tot, t_box, t_skw], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_tot, t_box, t_skw = (float(v) for v in t.cpu())
+    npx = pipe.forest_pixels_total()
+
+    # ---- end-to-end arm: pinned host weights in, all boxes + all spectra rows back to host, every step
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        host = pipe.make_host_buffers(W)
+        pipe.step_e2e(host, seed=7)
+        barrier()
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.time()
+        for i in range(n_e2e):
+            pipe.step_e2e(host, seed=8 + i)
+        barrier()
+        dt = (time.time() - t0) / n_e2e
+        e2e = {"value": cells / dt, "unit": "cells/s", "h2d_bytes_per_step": host["h2d_bytes"],
+               "d2h_bytes_per_step": host["d2h_bytes"], "ms_per_step": 1e3 * dt, "steps": n_e2e,
+               "skewer_pixels_per_s": npx / dt}
+        del host
+
+    # ---- roofline of the dominant kernel (slowest FFT pass), algorithmic bytes per launch
+    peak, how = measured_peak_hbm()
+    nk_bytes = pipe.bs.NX * pipe.bs.nyl * pipe.bs.nzh * 8          # this rank's half-complex box
+    nr_bytes = pipe.bs.nxl * pipe.bs.NY * pipe.bs.NZ * 4           # this rank's real box
+    alg = {"inv_x": 2 * nk_bytes + (4.0 / 13.0) * nk_bytes / 2, "inv_y": 2 * nk_bytes, "c2r_z": nk_bytes + nr_bytes,
+           "r2c_z": nk_bytes, "fwd_y": 2 * nk_bytes, "fwd_x": 2 * nk_bytes}
+    per = {k: (ms / n if n else 0.0) for k, (ms, n) in passes.items()}
+    dom = max(("inv_x", "inv_y", "c2r_z"), key=lambda k: per[k])
+    achieved = alg[dom] / (per[dom] * 1e-3) / 1e9 if per[dom] else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": how,
+                "passes_ms": per, "passes_gbs": {k: (alg[k] / (per[k] * 1e-3) / 1e9 if per[k] else None) for k in per},
+                "chunk_gbs": (332.0 * cells / world) / (t_box * 1e-3) / 1e9}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            cores = os.cpu_count()
+            r = cpu_oracle_step(256, cores)
+            cpu = {"value": r["value"], "unit": "cells/s", "cores": cores, "kind": "port",
+                   "sample": "256x256x1536 box (1/4 of the cells), 13 products with scipy.fft float32 workers=%d "
+                             "(pocketfft stands in for FFTW: pyfftw is not installable) + numba ReadSpec on 24 "
+                             "quasars/core extrapolated to the box's %d forest pixels" % (cores, r["npix_full"]),
+                   "t_boxes_s": r["t_boxes"], "t_skewers_s": r["t_skewers_extrapolated"],
+                   "skewer_pixels_per_s": r["skewer_pixels_per_s"], "grf_cells_per_s_boxes": r["cells"] / r["t_boxes"]}
+        line = {"metric": "grf_cells_per_s", "value": world * cells / world / (t_tot * 1e-3), "unit": "cells/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_tot,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "single chunk %dx%dx%d: Philox noise + r2c + 13 products (3 lognormal, delta, "
+                                       "6 eta, 3 velocity) + %d full-density skewers (gather 10 fields, delta_s, FGPA)"
+                                       % (nx, ny, NZ, len(ra)),
+                           "box": [nx, ny, NZ], "nqso": int(len(ra)), "forest_pixels": int(npx),
+                           "l2": "every pass streams >= 1.6 GB per launch, far above the 126 MB L2; no flush needed",
+                           "parallelism": "x-slabs over %d GPU(s), all-to-all transposes" % world},
+                "grf_cells_per_s_boxes": cells / (t_box * 1e-3), "box_cells_per_s": 13 * cells / (t_box * 1e-3),
+                "skewer_pixels_per_s": npx / (t_skw * 1e-3), "t_boxes_ms": t_box, "t_skewers_ms": t_skw,
+                "wall_s": wall, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": pipe.launches_per_step * args.steps,
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--box", type=int, default=0, help="NX=NY override (default: 512 per GPU, weak scaling)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,13 @@ size_t smk_box_elems(const smk_ctx* ctx);         /* float elements of this rank
 size_t smk_workspace_bytes(const smk_ctx* ctx);   /* bytes the ctx holds in HBM */
 int smk_sync(smk_ctx* ctx);                       /* cudaStreamSynchronize(ctx stream) */
 
+/* ---- per-pass device timing for the roofline report (bench.py).  When enabled, CUDA events are recorded on the
+ * ctx stream around every FFT pass kernel; smk_timing_collect synchronises the stream and returns, per pass
+ * (0 r2c-z, 1 forward-y, 2 forward-x, 3 inverse-x [with the fused multiply], 4 inverse-y, 5 c2r-z), the summed
+ * duration in ms and the number of launches since the last collect. */
+int smk_timing_enable(smk_ctx* ctx, int on);
+int smk_timing_collect(smk_ctx* ctx, double ms_sum[6], int count[6]);
+
 /* ---- white noise.  Replaces the np.random.normal plane loop of DrawGRF_boxk (make_boxes.py:46-48)
  * with Philox4x32-10 keyed by (seed, global cell index): identical for any slab decomposition. */
 int smk_noise_philox(smk_ctx* ctx, uint64_t seed, float* box_slab);
@@ -126,10 +133,11 @@ int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], 
  * noise: [nqso][nfft] float white noise, or NULL to draw Philox(seed, quasar index).  filt_rows: [nrows][nfft/2+1]
  * float = sqrt(max(P_miss(z_row,k),0)/pixsize); row_of_qso[q] selects the row (nearest tabulated z to z_eff).
  * zscale: [nqso][npix] or NULL; when NULL, sig_pix[npix]/sig_eff[q] is used (sigma_s(z)/sigma_s(z_eff)).
- * nfft must be a power of two in [256, 8192]. */
+ * qso_ids: [nqso] Philox stream id of each quasar (NULL: the row index), so that every rank that holds a piece of
+ * a sightline regenerates the same delta_s.  nfft must be a power of two in [256, 8192]. */
 int smk_smallscale(smk_ctx* ctx, int nqso, int nfft, int npix, const float* noise, uint64_t seed,
                    const float* filt_rows, const int* row_of_qso, const float* sig_pix, const float* sig_eff,
-                   float* delta_s);
+                   const long long* qso_ids, float* delta_s);
 
 /* ---- FGPA (util.py:421-433): F = exp(-a exp(b G (delta_l + delta_s + c eta_par))).  a,b,c,G are per-pixel
  * vectors [npix] (constant when -zfix is used).  delta_s / eta_par may be NULL (treated as 0). */

@@ -52,6 +52,18 @@ class BoxSynth(object):
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ per-pass device timing (bench.py roofline)
+    PASS_NAMES = ("r2c_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "c2r_z")
+
+    def timing_enable(self, on=True):
+        _lib.check(self.lib.smk_timing_enable(self.h, int(on)))
+
+    def timing_collect(self):
+        ms = (C.c_double * 6)()
+        n = (C.c_int * 6)()
+        _lib.check(self.lib.smk_timing_collect(self.h, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.PASS_NAMES)}
+
     # ------------------------------------------------------------------ allocation helpers
     def empty_boxk(self):
         return torch.zeros((self.NX, self.nyl, self.pitch), dtype=torch.complex64, device=self.device)

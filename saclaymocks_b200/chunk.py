@@ -1,0 +1,225 @@
+"""One chunk on one or several GPUs: make_boxes -> (boxes stay in HBM) -> make_spectra -> FGPA.
+
+Multi-GPU layout: every real product is x-slab sharded, rank g owning planes
+[g*NX/G, (g+1)*NX/G) (the decomposition make_spectra.py:220-221 uses for its slices); boxk stays in the
+transposed y-slab layout, so each 3-D transform needs exactly one all-to-all (torch.distributed / NCCL over
+NVLink).  Skewer pixels are computed by the rank whose slab owns them (make_spectra.py:443-448) after a halo
+exchange of dmax planes per side.  No data-path collective exists in the skewer stage besides that halo.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import spectra as sp
+from .boxes import BoxSynth, PRODUCTS, WEIGHT_OF
+
+_ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)   # noqa: E731
+
+
+class ChunkPipeline(object):
+    def __init__(self, NX, NY, NZ, dcell, device, rank=0, nranks=1, dmax=3, zfix=2.4, rsd=True, dla=True,
+                 group=None):
+        self.bs = BoxSynth(NX, NY, NZ, dcell, device=device, rank=rank, nranks=nranks)
+        self.device, self.rank, self.nranks, self.group = device, rank, nranks, group
+        self.geom = sp.SkewerGeometry(NX, NY, NZ, dcell, dmax=dmax)
+        self.eng = sp.SkewerEngine(self.geom, device=device)
+        self.fgpa = sp.FGPA(self.geom, zfix=zfix, device=device)
+        self.rsd, self.dla, self.dmax = rsd, dla, dmax
+        bs = self.bs
+        self.boxk = bs.empty_boxk()
+        # halo'd slabs: [halo_lo + nxl + halo_hi, NY, NZ]; global edges get no halo (make_spectra.py:220-221)
+        self.hlo = dmax if rank > 0 else 0
+        self.hhi = dmax if rank < nranks - 1 else 0
+        self.plane = bs.NY * bs.NZ
+        self.fields = {}
+        for name in PRODUCTS:
+            h = (self.hlo + self.hhi) if name in sp.FIELDS else 0
+            self.fields[name] = torch.empty((bs.nxl + h, bs.NY, bs.NZ), dtype=torch.float32, device=device)
+        self.stats = torch.zeros((len(PRODUCTS), 2), dtype=torch.float64, device=device)
+        if nranks > 1:
+            n = bs.NX * bs.nyl * bs.pitch
+            self.sendbuf = torch.empty(n, dtype=torch.complex64, device=device)
+            self.recvbuf = torch.empty(n, dtype=torch.complex64, device=device)
+        self.W = None
+        self.cat = None
+        # kernels per step: 3 forward passes + 13 x 3 inverse passes + gather + small-scale + FGPA
+        self.launches_per_step = 3 + 13 * 3 + 3
+
+    # ------------------------------------------------------------------ inputs
+    def set_weights(self, W):
+        """W: dict Pln1,Pln2,Pln3,P0 -> device float32 [NX, NY/R, NZ/2+1] (this rank's ky rows)."""
+        self.W = {k: self.bs.upload_weights(v) for k, v in W.items()}
+
+    def set_catalogue(self, ra, dec, z, ra0, dec0, ids=None):
+        g = self.geom
+        xyzr, nfor = sp.qso_lines_of_sight(g, ra, dec, z, ra0, dec0)
+        keep = nfor >= 0
+        xmin = g.LX * self.rank / self.nranks - g.LX / 2
+        xmax = g.LX * (self.rank + 1) / self.nranks - g.LX / 2
+        # sightline X runs monotonically from X*Rmin/R to X*Rmax_forest/R: keep quasars that can touch the slab
+        xa = xyzr[:, 0] * g.R_vec[0] / xyzr[:, 3]
+        xb = xyzr[:, 0] * g.R_vec[-1] / xyzr[:, 3]
+        touch = (np.minimum(xa, xb) <= xmax) & (np.maximum(xa, xb) > xmin)
+        sel = np.where(keep & touch)[0]
+        ids = np.arange(len(nfor), dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        self.cat = dict(sel=sel, xyzr=np.ascontiguousarray(xyzr[sel]), nfor=np.ascontiguousarray(nfor[sel]),
+                        ids=ids[sel], z=np.asarray(z)[sel], xmin=xmin, xmax=xmax, n_total=len(nfor))
+        nq, npix = len(sel), g.npixeltot
+        self.cat["xyzr_d"] = torch.as_tensor(self.cat["xyzr"], device=self.device)
+        self.cat["nfor_d"] = torch.as_tensor(self.cat["nfor"], device=self.device)
+        self.cat["nf_merge"] = self.fgpa.forest_count(self.cat["z"])
+        self.cat["prep"] = self.fgpa.prepare(self.cat["nf_merge"], self.cat["ids"])
+        self.out = tuple(torch.empty((nq, npix), dtype=torch.float32, device=self.device) for _ in range(4))
+        # pixels this rank owns: xmin < X <= xmax and inside the forest (for the pixel-rate metric)
+        own = 0
+        for i0 in range(0, nq, 4096):
+            X = self.cat["xyzr"][i0:i0 + 4096, 0:1] * g.R_vec[None, :] / self.cat["xyzr"][i0:i0 + 4096, 3:4]
+            inside = (X > xmin) & (X <= xmax) & (np.arange(npix)[None, :] < self.cat["nfor"][i0:i0 + 4096, None])
+            own += int(inside.sum())
+        self.cat["own_pixels"] = own
+
+    def forest_pixels_total(self):
+        t = torch.tensor([self.cat["own_pixels"]], dtype=torch.int64, device=self.device)
+        if self.nranks > 1:
+            torch.distributed.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    # ------------------------------------------------------------------ boxes
+    def _a2a(self):
+        torch.distributed.all_to_all_single(self.recvbuf, self.sendbuf, group=self.group)
+
+    def forward(self, seed, noise=None):
+        bs, L = self.bs, self.bs.lib
+        if self.nranks == 1:
+            _lib.check(L.smk_fft_r2c(bs.h, _ptr(noise), C.c_uint64(seed), _ptr(self.boxk)))
+        else:
+            _lib.check(L.smk_fft_r2c_local(bs.h, _ptr(noise), C.c_uint64(seed), _ptr(self.sendbuf)))
+            self._a2a()
+            _lib.check(L.smk_fft_r2c_finish(bs.h, _ptr(self.recvbuf), _ptr(self.boxk)))
+
+    def interior(self, name):
+        """The owned planes of a halo'd field buffer (contiguous view)."""
+        f = self.fields[name]
+        lo = self.hlo if name in sp.FIELDS else 0
+        return f[lo:lo + self.bs.nxl]
+
+    def product(self, name):
+        bs, L = self.bs, self.bs.lib
+        pid = _lib.PRODUCT_ID[name]
+        wt = self.W[WEIGHT_OF[name]] if name in WEIGHT_OF else None
+        out = self.interior(name)
+        st = self.stats[pid]
+        if self.nranks == 1:
+            _lib.check(L.smk_synth_c2r(bs.h, _ptr(self.boxk), pid, _ptr(wt), 1, C.c_double(bs.dgrowth0), _ptr(out),
+                                       _ptr(st)))
+        else:
+            _lib.check(L.smk_synth_c2r_local(bs.h, _ptr(self.boxk), pid, _ptr(wt), 1, C.c_double(bs.dgrowth0),
+                                             _ptr(self.sendbuf)))
+            self._a2a()
+            _lib.check(L.smk_synth_c2r_finish(bs.h, _ptr(self.recvbuf), _ptr(out), _ptr(st)))
+
+    def step_boxes(self, seed=0, noise=None, products=PRODUCTS):
+        self.stats.zero_()
+        self.forward(seed, noise)
+        for name in products:
+            self.product(name)
+
+    def sigmas(self):
+        """np.std of every product over the whole box (all ranks)."""
+        s = self.stats.clone()
+        if self.nranks > 1:
+            torch.distributed.all_reduce(s, group=self.group)
+        s = s.cpu().numpy()
+        n = float(self.bs.NX) * self.bs.NY * self.bs.NZ
+        return {name: float(np.sqrt(max(s[i, 1] / n - (s[i, 0] / n) ** 2, 0.0))) for i, name in enumerate(PRODUCTS)}
+
+    # ------------------------------------------------------------------ skewers
+    def halo_exchange(self):
+        """dmax planes per side of each of the 10 skewer fields to/from the x-neighbours."""
+        if self.nranks == 1:
+            return
+        import torch.distributed as dist
+        ops = []
+        d, nxl = self.dmax, self.bs.nxl
+        for name in sp.FIELDS:
+            f = self.fields[name]
+            if self.rank > 0:                       # lower neighbour
+                ops.append(dist.P2POp(dist.isend, f[self.hlo:self.hlo + d], self.rank - 1, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, f[0:d], self.rank - 1, group=self.group))
+            if self.rank < self.nranks - 1:         # upper neighbour
+                ops.append(dist.P2POp(dist.isend, f[self.hlo + nxl - d:self.hlo + nxl], self.rank + 1, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, f[self.hlo + nxl:self.hlo + nxl + d], self.rank + 1, group=self.group))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+    def step_skewers(self, seed=0, noise=None):
+        c = self.cat
+        self.halo_exchange()
+        nq, npix = len(c["sel"]), self.geom.npixeltot
+        if nq == 0:
+            return self.out
+        dl, ep, vp, F = self.out
+        fl = (C.c_void_p * 10)()
+        for i, k in enumerate(sp.FIELDS):
+            fl[i] = self.fields[k].data_ptr()
+        cg = self.geom.c_geom()
+        ix0 = self.rank * self.bs.nxl - self.hlo
+        nxs = self.bs.nxl + self.hlo + self.hhi
+        L = self.bs.lib
+        _lib.check(L.smk_skewers(self.bs.h, C.byref(cg), fl, ix0, nxs, C.c_double(c["xmin"]), C.c_double(c["xmax"]),
+                                 int(self.rsd), int(self.dla), nq, _ptr(c["xyzr_d"]), _ptr(c["nfor_d"]),
+                                 _ptr(self.eng.rvec), npix, _ptr(dl), _ptr(ep), _ptr(vp)))
+        ds = self.fgpa.small_scales(c["nf_merge"], noise=noise, seed=seed, prepared=c["prep"])
+        _lib.check(L.smk_fgpa(self.bs.h, nq, npix, _ptr(dl), _ptr(ds), _ptr(ep), _ptr(self.fgpa.G), _ptr(self.fgpa.a),
+                              _ptr(self.fgpa.b), _ptr(self.fgpa.c), _ptr(F)))
+        self.delta_s = ds
+        return self.out
+
+    def step(self, seed=0):
+        self.step_boxes(seed)
+        self.step_skewers(seed)
+
+    # ------------------------------------------------------------------ end-to-end through host buffers (1 GPU)
+    def make_host_buffers(self, W_dev):
+        bs = self.bs
+        host = {"W": {k: v.cpu().pin_memory() for k, v in W_dev.items()},
+                "box": [torch.empty((bs.NX, bs.NY, bs.NZ), dtype=torch.float32).pin_memory() for _ in range(2)],
+                "spec": [torch.empty(self.out[0].shape, dtype=torch.float32).pin_memory() for _ in range(4)],
+                "copy_stream": torch.cuda.Stream(device=self.device)}
+        host["h2d_bytes"] = sum(v.numel() * 4 for v in host["W"].values()) + self.cat["xyzr"].nbytes + self.cat["nfor"].nbytes
+        host["d2h_bytes"] = len(PRODUCTS) * bs.NX * bs.NY * bs.NZ * 4 + 4 * self.out[0].numel() * 4
+        return host
+
+    def step_e2e(self, host, seed=0):
+        """Host weight tables in (pinned), every box and every spectrum row out to host memory.  The two pinned box
+        buffers stand for the FITS writer's staging area; copies overlap the next product's transforms."""
+        assert self.nranks == 1
+        main = torch.cuda.current_stream(self.device)
+        cs = host["copy_stream"]
+        self.stats.zero_()
+        for k in self.W:
+            self.W[k].copy_(host["W"][k], non_blocking=True)
+        c = self.cat
+        c["xyzr_d"].copy_(torch.from_numpy(c["xyzr"]), non_blocking=True)
+        c["nfor_d"].copy_(torch.from_numpy(c["nfor"]), non_blocking=True)
+        self.forward(seed)
+        evs = []
+        for i, name in enumerate(PRODUCTS):
+            self.product(name)
+            e = torch.cuda.Event()
+            e.record(main)
+            cs.wait_event(e)
+            with torch.cuda.stream(cs):
+                host["box"][i & 1].copy_(self.interior(name), non_blocking=True)
+        self.step_skewers(seed)
+        e = torch.cuda.Event()
+        e.record(main)
+        cs.wait_event(e)
+        with torch.cuda.stream(cs):
+            for h, d in zip(host["spec"], self.out):
+                h.copy_(d, non_blocking=True)
+        cs.synchronize()
+        main.synchronize()
+        return host

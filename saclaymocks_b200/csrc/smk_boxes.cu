@@ -131,7 +131,7 @@ static int launch_strided_n(bool inv, int mul, const StridedParams& p, int noute
   return SMK_ERR_ARG;
 }
 
-#define SMK_STRIDED_SIZES(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2560)
+#define SMK_STRIDED_SIZES(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(2560)
 
 bool strided_size_supported(int n) {
 #define X(N_) if (n == N_) return true;

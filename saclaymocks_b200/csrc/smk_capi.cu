@@ -23,7 +23,28 @@ struct smk_ctx {
   float2* work = nullptr;      // [nxl][ny][pitch] (== boxk size)
   double* stats = nullptr;     // scratch for the host wrapper
   size_t bytes = 0;
+  // optional per-pass CUDA-event timing (smk_timing_*): events are recorded around every pass kernel
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;       // pool
+  std::vector<int> ev_pass;          // pass id of the interval that STARTS at event i (-1 = none)
+  size_t ev_used = 0;
 };
+
+enum { PASS_R2C_Z = 0, PASS_FWD_Y, PASS_FWD_X, PASS_INV_X, PASS_INV_Y, PASS_C2R_Z, PASS_COUNT };
+
+// record an event; `pass` names the kernel launched right after it (-1: closes the previous interval only)
+static void tmark(smk_ctx* c, int pass) {
+  if (!c->timing) return;
+  if (c->ev_used == c->ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev.push_back(e);
+    c->ev_pass.push_back(-1);
+  }
+  cudaEventRecord(c->ev[c->ev_used], c->stream);
+  c->ev_pass[c->ev_used] = pass;
+  ++c->ev_used;
+}
 
 static int make_twiddles(int n, float2** dptr, size_t* bytes) {
   std::vector<float2> h(n);
@@ -99,6 +120,7 @@ int smk_ctx_destroy(smk_ctx* c) {
   cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->tw_z);
   cudaFree(c->kx); cudaFree(c->ky); cudaFree(c->kz);
   cudaFree(c->work); cudaFree(c->stats);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
   return SMK_OK;
 }
@@ -112,6 +134,27 @@ int smk_sync(smk_ctx* c) {
   return SMK_OK;
 }
 
+int smk_timing_enable(smk_ctx* c, int on) {
+  c->timing = on != 0;
+  c->ev_used = 0;
+  return SMK_OK;
+}
+
+int smk_timing_collect(smk_ctx* c, double ms_sum[6], int count[6]) {
+  for (int i = 0; i < PASS_COUNT; ++i) { ms_sum[i] = 0.0; count[i] = 0; }
+  SMK_CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i + 1 < c->ev_used; ++i) {
+    int p = c->ev_pass[i];
+    if (p < 0) continue;
+    float ms = 0.f;
+    SMK_CUDA_OK(cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+    ms_sum[p] += ms;
+    count[p] += 1;
+  }
+  c->ev_used = 0;
+  return SMK_OK;
+}
+
 int smk_noise_philox(smk_ctx* c, uint64_t seed, float* box_slab) {
   long long ncells = (long long)c->nxl * c->ny * c->nz;
   return launch_philox_fill(box_slab, ncells, seed, (long long)c->rank * ncells, c->stream);
@@ -122,22 +165,29 @@ int smk_fft_r2c_local(smk_ctx* c, const float* box_slab, uint64_t seed, void* se
   long long nlines = (long long)c->nxl * c->ny;
   long long cell0 = (long long)c->rank * nlines * c->nz;
   float2* tmp = (c->nranks == 1) ? (float2*)sendbuf : c->work;
+  tmark(c, PASS_R2C_Z);
   int rc = launch_r2c_z(c->nz, box_slab, tmp, nlines, c->pitch, c->tw_z, box_slab == nullptr, seed, cell0, c->stream);
   if (rc) return rc;
+  tmark(c, PASS_FWD_Y);
   // y pass: outer = local x plane; output into [dest][xl][yl][z] (dest = y / nyl)
   PassAddr ain{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
   PassAddr aout{(long long)c->nyl * c->pitch, (long long)c->nxl * c->nyl * c->pitch, (long long)c->pitch, c->nyl};
   MulArgs m{};
-  return launch_c2c_strided(c->ny, false, MUL_NONE, tmp, (float2*)sendbuf, ain, aout, c->nxl, c->pitch, m, c->tw_y,
-                            c->stream);
+  rc = launch_c2c_strided(c->ny, false, MUL_NONE, tmp, (float2*)sendbuf, ain, aout, c->nxl, c->pitch, m, c->tw_y,
+                          c->stream);
+  tmark(c, -1);
+  return rc;
 }
 
 int smk_fft_r2c_finish(smk_ctx* c, const void* recvbuf, void* boxk) {
   // x pass on [nx][nyl][pitch]: outer = local y
   PassAddr a{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
   MulArgs m{};
-  return launch_c2c_strided(c->nx, false, MUL_NONE, (const float2*)recvbuf, (float2*)boxk, a, a, c->nyl, c->pitch, m,
-                            c->tw_x, c->stream);
+  tmark(c, PASS_FWD_X);
+  int rc = launch_c2c_strided(c->nx, false, MUL_NONE, (const float2*)recvbuf, (float2*)boxk, a, a, c->nyl, c->pitch, m,
+                              c->tw_x, c->stream);
+  tmark(c, -1);
+  return rc;
 }
 
 int smk_fft_r2c(smk_ctx* c, const float* box_slab, uint64_t seed, void* boxk) {
@@ -171,8 +221,11 @@ int smk_synth_c2r_local(smk_ctx* c, void* boxk, int product, const float* wtable
     m.vscale = dgrowth0;
   }
   PassAddr a{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
-  return launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, (float2*)sendbuf, a, a, c->nyl, c->nzh, m, c->tw_x,
-                            c->stream);
+  tmark(c, PASS_INV_X);
+  int rc = launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, (float2*)sendbuf, a, a, c->nyl, c->nzh, m,
+                              c->tw_x, c->stream);
+  tmark(c, -1);
+  return rc;
 }
 
 int smk_synth_c2r_finish(smk_ctx* c, void* recvbuf, float* out_slab, double* stats) {
@@ -181,11 +234,15 @@ int smk_synth_c2r_finish(smk_ctx* c, void* recvbuf, float* out_slab, double* sta
   PassAddr aout{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
   float2* tmp = (c->nranks == 1) ? (float2*)recvbuf : c->work;
   MulArgs m{};
+  tmark(c, PASS_INV_Y);
   int rc = launch_c2c_strided(c->ny, true, MUL_NONE, (const float2*)recvbuf, tmp, ain, aout, c->nxl, c->nzh, m,
                               c->tw_y, c->stream);
   if (rc) return rc;
   float norm = (float)((double)c->nx * c->ny * c->nz);
-  return launch_c2r_z(c->nz, tmp, out_slab, (long long)c->nxl * c->ny, c->pitch, c->tw_z, norm, stats, c->stream);
+  tmark(c, PASS_C2R_Z);
+  rc = launch_c2r_z(c->nz, tmp, out_slab, (long long)c->nxl * c->ny, c->pitch, c->tw_z, norm, stats, c->stream);
+  tmark(c, -1);
+  return rc;
 }
 
 int smk_synth_c2r(smk_ctx* c, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,

@@ -20,6 +20,7 @@ struct SmallScaleParams {
   const float* sig_pix;    // [npix]
   const float* sig_eff;    // [nqso]
   float* delta_s;          // [nqso][npix]
+  const long long* ids;    // [nqso] Philox stream id per quasar (null: the row index)
   const float2* tw;        // W_nfft
 };
 
@@ -37,7 +38,8 @@ __global__ void __launch_bounds__(M >= 2048 ? 512 : (M >= 512 ? 256 : 64)) small
     for (int n = threadIdx.x; n < M; n += NT) sm[n] = __ldg(in2 + n);
   } else {
     for (int c = threadIdx.x; c < M / 2; c += NT) {
-      float4 g = philox_normal4(p.seed ^ 0x5ca1ab1e5eedULL, (uint64_t)q * (uint64_t)(M / 2) + c);
+      uint64_t id = p.ids ? (uint64_t)p.ids[q] : (uint64_t)q;
+      float4 g = philox_normal4(p.seed ^ 0x5ca1ab1e5eedULL, id * (uint64_t)(M / 2) + c);
       sm[2 * c] = make_float2(g.x, g.y);
       sm[2 * c + 1] = make_float2(g.z, g.w);
     }
@@ -135,11 +137,11 @@ static int tw1d(int nfft, const float2** out) {
 
 extern "C" int smk_smallscale(smk_ctx* ctx, int nqso, int nfft, int npix, const float* noise, uint64_t seed,
                               const float* filt_rows, const int* row_of_qso, const float* sig_pix,
-                              const float* sig_eff, float* delta_s) {
+                              const float* sig_eff, const long long* qso_ids, float* delta_s) {
   using namespace smk;
   if (nqso == 0) return SMK_OK;
   if (!filt_rows || !row_of_qso || !delta_s || npix > nfft) { set_error("smk_smallscale: bad argument"); return SMK_ERR_ARG; }
-  SmallScaleParams p{nqso, npix, noise, seed, filt_rows, row_of_qso, sig_pix, sig_eff, delta_s, nullptr};
+  SmallScaleParams p{nqso, npix, noise, seed, filt_rows, row_of_qso, sig_pix, sig_eff, delta_s, qso_ids, nullptr};
   int rc = tw1d(nfft, &p.tw);
   if (rc) return rc;
   cudaStream_t st = smk_ctx_stream(ctx);

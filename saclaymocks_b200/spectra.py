@@ -176,26 +176,36 @@ class FGPA(object):
         means = np.array([self.z[:k].mean() for k in uniq])
         return means[inv]
 
-    def small_scales(self, nforest, noise=None, seed=0):
+    def small_scales(self, nforest, noise=None, seed=0, qso_ids=None, prepared=None):
         """delta_s [nqso, npix] (zero rows for quasars with an empty forest, merge_spectra.py:327-330)."""
         nq, npix = len(nforest), self.geom.npixeltot
         nfft = self.nfft_for(npix)
-        zeff = self.zeff(nforest)
-        rows = np.array([self.p1d.iz(z) for z in zeff], dtype=np.int32)
-        sig_eff = np.float32(cosmo_mod.lin_interp(self.p1d.z, self.p1d.sigma, zeff))
+        if prepared is None:
+            prepared = self.prepare(nforest, qso_ids)
+        rows_t, sig_eff_t, ids_t, empty = prepared          # device tensors kept alive by the caller / this frame
         d = torch.empty((nq, npix), dtype=torch.float32, device=self.device)
         nz_t = None
         if noise is not None:
             nz_t = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32), device=self.device)
             assert tuple(nz_t.shape) == (nq, nfft)
-        rows_t = torch.as_tensor(rows, device=self.device)          # keep alive across the call
-        sig_eff_t = torch.as_tensor(sig_eff, device=self.device)
         _lib.check(self.lib.smk_smallscale(None, nq, nfft, npix, _ptr(nz_t), C.c_uint64(seed), _ptr(self.filt_rows(nfft)),
-                                           _ptr(rows_t), _ptr(self.sig_pix), _ptr(sig_eff_t), _ptr(d)))
-        empty = torch.as_tensor(np.asarray(nforest) <= 0, device=self.device)
-        if bool(empty.any()):
+                                           _ptr(rows_t), _ptr(self.sig_pix), _ptr(sig_eff_t), _ptr(ids_t), _ptr(d)))
+        if empty is not None:
             d[empty] = 0
         return d
+
+    def prepare(self, nforest, qso_ids=None):
+        """Per-quasar inputs of the small-scale kernel: P1D_miss table row (nearest tabulated z to z_eff), sigma_s(z_eff),
+        Philox stream ids, and the mask of empty forests."""
+        zeff = self.zeff(nforest)
+        rows = np.array([self.p1d.iz(z) for z in np.unique(zeff)], dtype=np.int32)[np.unique(zeff, return_inverse=True)[1]]
+        sig_eff = np.float32(cosmo_mod.lin_interp(self.p1d.z, self.p1d.sigma, zeff))
+        rows_t = torch.as_tensor(rows, device=self.device)
+        sig_eff_t = torch.as_tensor(sig_eff, device=self.device)
+        ids_t = None if qso_ids is None else torch.as_tensor(np.asarray(qso_ids, dtype=np.int64), device=self.device)
+        em = np.asarray(nforest) <= 0
+        empty = torch.as_tensor(em, device=self.device) if em.any() else None
+        return rows_t, sig_eff_t, ids_t, empty
 
     def flux(self, delta_l, delta_s=None, eta_par=None):
         nq, npix = delta_l.shape
