@@ -30,86 +30,98 @@ struct StridedParams {
   const float2* in;
   float2* out;
   PassAddr ain, aout;
-  int ncols;
+  int ncols;       // multiple of LINES (the padded pitch)
+  int wcols;       // valid columns of the weight table rows (nz/2+1)
   MulArgs mul;
   const float2* tw;
 };
 
+// element offset of point n: plain stride, or the two-level [hi][lo] form left behind by an all-to-all
+template <bool SPLIT>
 __device__ __forceinline__ long long point_off(const PassAddr& a, int n) {
+  if (!SPLIT) return (long long)n * a.lo_stride;
   int hi = n / a.nsplit;
   int lo = n - hi * a.nsplit;
   return hi * a.hi_stride + lo * a.lo_stride;
 }
 
-// factor of make_boxes.py:299-306,324-429 in the reference's float32 rounding order
-template <int MUL>
-__device__ __forceinline__ float2 apply_mul(float2 v, const MulArgs& m, int n, int outer, int col, long long in_off,
-                                            bool col_ok) {
-  if (MUL == MUL_NONE) return v;
-  if (MUL == MUL_TABLE) {
-    float w = col_ok ? __ldg(m.wt + n * m.wt_n_stride + outer * m.wt_outer_stride + col) : 0.f;
-    v = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
-    if (m.store_back != nullptr && col_ok) m.store_back[in_off] = v;
-    return v;
-  }
-  float kx = __ldg(m.kn + n), ky = __ldg(m.ko + outer + m.outer0), kz = col_ok ? __ldg(m.kc + col) : 0.f;
-  float kk = __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
-  if (n == 0 && outer + m.outer0 == 0 && col == 0) kk = 1.f;
-  float ka = m.fa == 0 ? kx : (m.fa == 1 ? ky : kz);
-  float kb = m.fb == 0 ? kx : (m.fb == 1 ? ky : kz);
-  if (MUL == MUL_ETA) {
-    float f = __fdiv_rn(__fmul_rn(ka, kb), kk);
-    return make_float2(__fmul_rn(v.x, f), __fmul_rn(v.y, f));
-  }
-  // MUL_VEL: boxk *= -1j*k/kk*H0*dgrowth0 -- float32 up to "*H0", then float64 (numpy promotes on the
-  // float64 scalar dgrowth0 and rounds the complex128 product back to complex64)
-  float f32 = __fmul_rn(__fdiv_rn(-ka, kk), 100.0f);
-  double f = (double)f32 * m.vscale;   // vscale = dgrowth0 (H0 = 100 is applied above in float32)
-  return make_float2((float)(-(double)v.y * f), (float)((double)v.x * f));
-}
-
-template <int N, bool INV, int MUL>
-__global__ void __launch_bounds__(StridedTraits<N>::NT) c2c_strided_kernel(StridedParams p) {
+template <int N, bool INV, int MUL, bool SPLIT_IN, bool SPLIT_OUT>
+__global__ void __launch_bounds__(StridedTraits<N>::NT) c2c_strided_kernel(const __grid_constant__ StridedParams p) {
   using P = typename PlanFor<N>::type;
   constexpr int LINES = StridedTraits<N>::LINES;
   constexpr int NT = StridedTraits<N>::NT;
+  constexpr int R0 = P::radix(0);
+  constexpr int TPT0 = (N / R0 * LINES + NT - 1) / NT;
   extern __shared__ float2 sm[];   // [N][LINES]
-  const int col0 = blockIdx.x * LINES;
+  const int col = blockIdx.x * LINES + threadIdx.x % LINES;   // this thread's kz column (fixed for the kernel)
   const int outer = blockIdx.y;
-  const long long ibase = outer * p.ain.outer_stride + col0;
-  const long long obase = outer * p.aout.outer_stride + col0;
-  const int ncols = p.ncols;
+  const float2* __restrict__ inl = p.in + (outer * p.ain.outer_stride + col);
+  float2* __restrict__ outl = p.out + (outer * p.aout.outer_stride + col);
 
-  auto ld_g = [&](int line, int n) {
-    long long off = ibase + point_off(p.ain, n) + line;
-    bool ok = (col0 + line) < ncols;
-    float2 v = ok ? p.in[off] : make_float2(0.f, 0.f);
-    return apply_mul<MUL>(v, p.mul, n, outer, col0 + line, off, ok);
+  // ---- fused multiply of make_boxes.py:247-429 (reference float32 rounding order), applied to the loaded element
+  float wv[MUL == MUL_TABLE ? TPT0 : 1][MUL == MUL_TABLE ? R0 : 1];
+  const float* __restrict__ wtl = nullptr;
+  float2* __restrict__ sbl = nullptr;
+  float ky = 0.f, kz = 0.f, ky2 = 0.f, kz2 = 0.f;
+  if (MUL == MUL_TABLE) {
+    wtl = p.mul.wt + (outer * p.mul.wt_outer_stride + min(col, p.wcols - 1));
+    if (p.mul.store_back) sbl = p.mul.store_back + (outer * p.ain.outer_stride + col);
+  } else if (MUL == MUL_ETA || MUL == MUL_VEL) {
+    ky = __ldg(p.mul.ko + outer + p.mul.outer0);
+    kz = col < p.wcols ? __ldg(p.mul.kc + col) : 0.f;
+    ky2 = __fmul_rn(ky, ky);
+    kz2 = __fmul_rn(kz, kz);
+  }
+  auto ld_g = [&](int, int n, int i, int t) {
+    if (MUL == MUL_TABLE) wv[i][t] = __ldg(wtl + n * p.mul.wt_n_stride);
+    return inl[point_off<SPLIT_IN>(p.ain, n)];
   };
-  auto st_g = [&](int line, int k, float2 val) {
-    if ((col0 + line) < ncols) p.out[obase + point_off(p.aout, k) + line] = val;
+  auto pre = [&](int, int n, int i, int t, float2 v) {
+    if (MUL == MUL_NONE) return v;
+    if (MUL == MUL_TABLE) {
+      float w = col < p.wcols ? wv[i][t] : 0.f;
+      v = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
+      if (sbl) sbl[point_off<SPLIT_IN>(p.ain, n)] = v;
+      return v;
+    }
+    const float kx = __ldg(p.mul.kn + n);
+    float kk = __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), ky2), kz2);      // (kx*kx + ky*ky) + kz*kz
+    if (n == 0 && outer + p.mul.outer0 == 0 && col == 0) kk = 1.f;     // make_boxes.py:306
+    const float ka = p.mul.fa == 0 ? kx : (p.mul.fa == 1 ? ky : kz);
+    if (MUL == MUL_ETA) {
+      const float kb = p.mul.fb == 0 ? kx : (p.mul.fb == 1 ? ky : kz);
+      const float f = __fdiv_rn(__fmul_rn(ka, kb), kk);
+      return make_float2(__fmul_rn(v.x, f), __fmul_rn(v.y, f));
+    }
+    // MUL_VEL: boxk *= -1j*k/kk*H0*dgrowth0 -- float32 up to "*H0", then float64 (numpy promotes on the float64
+    // scalar dgrowth0 and rounds the complex128 product back to complex64)
+    const float f32 = __fmul_rn(__fdiv_rn(-ka, kk), 100.0f);
+    const double f = (double)f32 * p.mul.vscale;
+    return make_float2((float)(-(double)v.y * f), (float)((double)v.x * f));
   };
+  auto st_g = [&](int, int k, float2 val) { outl[point_off<SPLIT_OUT>(p.aout, k)] = val; };
   auto st_s = [&](int line, int pos, float2 val) { sm[pos * LINES + line] = val; };
-  auto ld_s = [&](int line, int pos) { return sm[pos * LINES + line]; };
+  auto ld_s = [&](int line, int pos, int, int) { return sm[pos * LINES + line]; };
 
   if constexpr (P::S == 1) {
-    dif_stage<P, 0, INV, LINES, NT, OUT_NATURAL>(ld_g, st_g, p.tw, 1);
+    dif_stage<P, 0, INV, LINES, NT, OUT_NATURAL>(ld_g, st_g, p.tw, 1, pre);
   } else {
-    dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE>(ld_g, st_s, p.tw, 1);
+    dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE>(ld_g, st_s, p.tw, 1, pre);
     __syncthreads();
     dif_stages_smem<P, 1, P::S - 1, INV, LINES, 1, LINES, NT>(sm, p.tw, 1);
     dif_stage<P, P::S - 1, INV, LINES, NT, OUT_NATURAL>(ld_s, st_g, p.tw, 1);
   }
 }
 
-template <int N, bool INV, int MUL>
+template <int N, bool INV, int MUL, bool SPLIT_IN, bool SPLIT_OUT>
 static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st) {
   constexpr int LINES = StridedTraits<N>::LINES;
   constexpr int NT = StridedTraits<N>::NT;
   size_t smem = (size_t)N * LINES * sizeof(float2);
-  auto kern = c2c_strided_kernel<N, INV, MUL>;
+  auto kern = c2c_strided_kernel<N, INV, MUL, SPLIT_IN, SPLIT_OUT>;
   if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((p.ncols + LINES - 1) / LINES, nouter);
+  if (p.ncols % LINES) { set_error("strided pass: column count must be a multiple of the tile width"); return SMK_ERR_ARG; }
+  dim3 grid(p.ncols / LINES, nouter);
   kern<<<grid, NT, smem, st>>>(p);
   SMK_CUDA_OK(cudaGetLastError());
   return SMK_OK;
@@ -117,17 +129,22 @@ static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st)
 
 template <int N>
 static int launch_strided_n(bool inv, int mul, const StridedParams& p, int nouter, cudaStream_t st) {
+  const bool si = p.ain.nsplit < N, so = p.aout.nsplit < N;
   if (!inv) {
-    if (mul != MUL_NONE) { set_error("forward pass takes no multiplier"); return SMK_ERR_ARG; }
-    return launch_strided_t<N, false, MUL_NONE>(p, nouter, st);
+    if (mul != MUL_NONE || si) { set_error("forward pass: unsupported variant"); return SMK_ERR_ARG; }
+    return so ? launch_strided_t<N, false, MUL_NONE, false, true>(p, nouter, st)
+              : launch_strided_t<N, false, MUL_NONE, false, false>(p, nouter, st);
   }
+  if (so) { set_error("inverse pass: unsupported variant"); return SMK_ERR_ARG; }
   switch (mul) {
-    case MUL_NONE: return launch_strided_t<N, true, MUL_NONE>(p, nouter, st);
-    case MUL_TABLE: return launch_strided_t<N, true, MUL_TABLE>(p, nouter, st);
-    case MUL_ETA: return launch_strided_t<N, true, MUL_ETA>(p, nouter, st);
-    case MUL_VEL: return launch_strided_t<N, true, MUL_VEL>(p, nouter, st);
+    case MUL_NONE:
+      return si ? launch_strided_t<N, true, MUL_NONE, true, false>(p, nouter, st)
+                : launch_strided_t<N, true, MUL_NONE, false, false>(p, nouter, st);
+    case MUL_TABLE: if (si) break; return launch_strided_t<N, true, MUL_TABLE, false, false>(p, nouter, st);
+    case MUL_ETA: if (si) break; return launch_strided_t<N, true, MUL_ETA, false, false>(p, nouter, st);
+    case MUL_VEL: if (si) break; return launch_strided_t<N, true, MUL_VEL, false, false>(p, nouter, st);
   }
-  set_error("bad multiplier mode");
+  set_error("bad multiplier mode / addressing combination");
   return SMK_ERR_ARG;
 }
 
@@ -141,8 +158,8 @@ bool strided_size_supported(int n) {
 }
 
 int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, float2* out, PassAddr ain, PassAddr aout,
-                       int nouter, int ncols, const MulArgs& mul, const float2* tw, cudaStream_t st) {
-  StridedParams p{in, out, ain, aout, ncols, mul, tw};
+                       int nouter, int ncols, int wcols, const MulArgs& mul, const float2* tw, cudaStream_t st) {
+  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw};
   switch (N) {
 #define X(N_) case N_: return launch_strided_n<N_>(inverse, mul_mode, p, nouter, st);
     SMK_STRIDED_SIZES(X)
@@ -191,9 +208,12 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
     }
   } else {
     const float2* in2 = reinterpret_cast<const float2*>(p.in);
-    for (int idx = threadIdx.x; idx < LINES * M; idx += NT) {
-      int line = idx / M, n = idx - line * M;
-      if (line0 + line < p.nlines) sm[line * LP + n] = __ldg(in2 + (line0 + line) * M + n);
+    for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {      // one warp per line: no index division
+      if (line0 + line < p.nlines) {
+        const float2* src = in2 + (line0 + line) * M;
+#pragma unroll 8
+        for (int n = threadIdx.x & 31; n < M; n += 32) sm[line * LP + n] = __ldg(src + n);
+      }
     }
   }
   __syncthreads();
@@ -217,10 +237,13 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
     if (k != M - k) row[M - k] = xm;
   }
   __syncthreads();
-  // ---- store M+1 complex per line
-  for (int idx = threadIdx.x; idx < LINES * (M + 1); idx += NT) {
-    int line = idx / (M + 1), k = idx - line * (M + 1);
-    if (line0 + line < p.nlines) p.out[(line0 + line) * p.pitch + k] = sm[line * LP + k];
+  // ---- store M+1 complex per line (row pads are zeroed so that later passes may stream whole rows)
+  for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
+    if (line0 + line < p.nlines) {
+      float2* dst = p.out + (line0 + line) * p.pitch;
+#pragma unroll 8
+      for (int k = threadIdx.x & 31; k < p.pitch; k += 32) dst[k] = (k <= M) ? sm[line * LP + k] : make_float2(0.f, 0.f);
+    }
   }
 }
 
@@ -241,11 +264,11 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
   extern __shared__ float2 sm[];
   __shared__ double red[2][NT / 32];
   const long long line0 = (long long)blockIdx.x * LINES;
-  for (int idx = threadIdx.x; idx < LINES * (M + 1); idx += NT) {
-    int line = idx / (M + 1), k = idx - line * (M + 1);
-    float2 v = make_float2(0.f, 0.f);
-    if (line0 + line < p.nlines) v = __ldg(p.in + (line0 + line) * p.pitch + k);
-    sm[line * LP + k] = v;
+  for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {        // one warp per line: no index division
+    const bool ok = line0 + line < p.nlines;
+    const float2* src = p.in + (line0 + line) * p.pitch;
+#pragma unroll 8
+    for (int k = threadIdx.x & 31; k <= M; k += 32) sm[line * LP + k] = ok ? __ldg(src + k) : make_float2(0.f, 0.f);
   }
   __syncthreads();
   // ---- Z[k] = A + iB, A = X[k] + conj(X[M-k]), B = (X[k] - conj(X[M-k])) w^-k ; imaginary parts of the
@@ -270,15 +293,18 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
   // ---- store x[2n], x[2n+1] = z[n] / N, accumulate sum and sum of squares
   float s1 = 0.f, s2 = 0.f;
   float2* out2 = reinterpret_cast<float2*>(p.out);
-  for (int idx = threadIdx.x; idx < LINES * M; idx += NT) {
-    int line = idx / M, n = idx - line * M;
+  for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
     if (line0 + line < p.nlines) {
-      float2 z = sm[line * LP + n];
-      z.x = __fdiv_rn(z.x, p.norm);
-      z.y = __fdiv_rn(z.y, p.norm);
-      out2[(line0 + line) * M + n] = z;
-      s1 += z.x + z.y;
-      s2 += z.x * z.x + z.y * z.y;
+      float2* dst = out2 + (line0 + line) * M;
+#pragma unroll 8
+      for (int n = threadIdx.x & 31; n < M; n += 32) {
+        float2 z = sm[line * LP + n];
+        z.x = __fdiv_rn(z.x, p.norm);
+        z.y = __fdiv_rn(z.y, p.norm);
+        dst[n] = z;
+        s1 += z.x + z.y;
+        s2 += z.x * z.x + z.y * z.y;
+      }
     }
   }
   if (p.stats != nullptr) {

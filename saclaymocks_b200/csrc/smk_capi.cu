@@ -173,7 +173,7 @@ int smk_fft_r2c_local(smk_ctx* c, const float* box_slab, uint64_t seed, void* se
   PassAddr ain{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
   PassAddr aout{(long long)c->nyl * c->pitch, (long long)c->nxl * c->nyl * c->pitch, (long long)c->pitch, c->nyl};
   MulArgs m{};
-  rc = launch_c2c_strided(c->ny, false, MUL_NONE, tmp, (float2*)sendbuf, ain, aout, c->nxl, c->pitch, m, c->tw_y,
+  rc = launch_c2c_strided(c->ny, false, MUL_NONE, tmp, (float2*)sendbuf, ain, aout, c->nxl, c->pitch, c->nzh, m, c->tw_y,
                           c->stream);
   tmark(c, -1);
   return rc;
@@ -184,7 +184,7 @@ int smk_fft_r2c_finish(smk_ctx* c, const void* recvbuf, void* boxk) {
   PassAddr a{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
   MulArgs m{};
   tmark(c, PASS_FWD_X);
-  int rc = launch_c2c_strided(c->nx, false, MUL_NONE, (const float2*)recvbuf, (float2*)boxk, a, a, c->nyl, c->pitch, m,
+  int rc = launch_c2c_strided(c->nx, false, MUL_NONE, (const float2*)recvbuf, (float2*)boxk, a, a, c->nyl, c->pitch, c->nzh, m,
                               c->tw_x, c->stream);
   tmark(c, -1);
   return rc;
@@ -222,7 +222,7 @@ int smk_synth_c2r_local(smk_ctx* c, void* boxk, int product, const float* wtable
   }
   PassAddr a{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
   tmark(c, PASS_INV_X);
-  int rc = launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, (float2*)sendbuf, a, a, c->nyl, c->nzh, m,
+  int rc = launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, (float2*)sendbuf, a, a, c->nyl, c->pitch, c->nzh, m,
                               c->tw_x, c->stream);
   tmark(c, -1);
   return rc;
@@ -235,7 +235,7 @@ int smk_synth_c2r_finish(smk_ctx* c, void* recvbuf, float* out_slab, double* sta
   float2* tmp = (c->nranks == 1) ? (float2*)recvbuf : c->work;
   MulArgs m{};
   tmark(c, PASS_INV_Y);
-  int rc = launch_c2c_strided(c->ny, true, MUL_NONE, (const float2*)recvbuf, tmp, ain, aout, c->nxl, c->nzh, m,
+  int rc = launch_c2c_strided(c->ny, true, MUL_NONE, (const float2*)recvbuf, tmp, ain, aout, c->nxl, c->pitch, c->nzh, m,
                               c->tw_y, c->stream);
   if (rc) return rc;
   float norm = (float)((double)c->nx * c->ny * c->nz);

@@ -191,8 +191,16 @@ SMK_PLAN(4096, 8, 8, 8, 8)
 // tw is the table W_L, L = N * twmul.
 enum { OUT_INPLACE = 0, OUT_NATURAL = 1, OUT_RESORT = 2 };
 
-template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store>
-__device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __restrict__ tw, int twmul) {
+struct NoPre {
+  __device__ __forceinline__ float2 operator()(int, int, int, int, float2 v) const { return v; }
+};
+
+// ld(line, pos, i, t): i = task slot of this thread, t = input index of the butterfly (both compile-time after
+// unrolling, so a caller can keep per-element side data in a register array indexed [i][t]);
+// pre(line, pos, i, t, v) runs after ALL loads of the thread have been issued (fused multiply of the first stage).
+template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store, class Pre = NoPre>
+__device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __restrict__ tw, int twmul,
+                                          Pre pre = Pre()) {
   constexpr int R = P::radix(STAGE);
   constexpr int M = P::sub(STAGE);
   constexpr int MQ = M / R;
@@ -200,38 +208,44 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
   constexpr int NTASK = NB * LINES;
   constexpr bool LAST = (STAGE == P::S - 1);
   static_assert(OUT == OUT_INPLACE || LAST, "natural-order store only on the last stage");
+  static_assert(NT % LINES == 0, "threads per block must be a multiple of the lines per tile");
   constexpr int TPT = (NTASK + NT - 1) / NT;
   constexpr bool EVEN = (NTASK % NT == 0);
+  constexpr int JSTEP = NT / LINES;
+  // a thread always works on the same line: task = threadIdx.x + i*NT  =>  line = threadIdx.x % LINES
+  const int line = threadIdx.x % LINES;
+  const int j0 = threadIdx.x / LINES;
   // phase 1: all loads of this thread (keeps TPT*R independent loads in flight)
   float2 v[TPT][R];
 #pragma unroll
   for (int i = 0; i < TPT; ++i) {
-    int task = threadIdx.x + i * NT;
-    if (EVEN || task < NTASK) {
-      int line = task % LINES, j = task / LINES;
-      int b = j / MQ, o = j - b * MQ;
+    const int j = j0 + i * JSTEP;
+    if (EVEN || j < NB) {
+      const int b = j / MQ, o = j - b * MQ;
 #pragma unroll
-      for (int t = 0; t < R; ++t) v[i][t] = ld(line, b * M + o + t * MQ);
+      for (int t = 0; t < R; ++t) v[i][t] = ld(line, b * M + o + t * MQ, i, t);
     }
   }
   if (OUT == OUT_RESORT) __syncthreads();
 #pragma unroll
   for (int i = 0; i < TPT; ++i) {
-    int task = threadIdx.x + i * NT;
-    if (EVEN || task < NTASK) {
-      int line = task % LINES, j = task / LINES;
-      int b = j / MQ, o = j - b * MQ;
+    const int j = j0 + i * JSTEP;
+    if (EVEN || j < NB) {
+      const int b = j / MQ, o = j - b * MQ;
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[i][t] = pre(line, b * M + o + t * MQ, i, t, v[i][t]);
       Butterfly<R, INV>::run(v[i]);
       if (!LAST) {
+        const int oc = o * ((P::N / M) * twmul);   // W_sub^(o q) = W_L[q * oc]
 #pragma unroll
         for (int q = 1; q < R; ++q) {
-          float2 w = __ldg(tw + (o * q * (P::N / M)) * twmul);
+          float2 w = __ldg(tw + q * oc);
           if (INV) w.y = -w.y;
           v[i][q] = cmul(v[i][q], w);
         }
       }
       if (OUT != OUT_INPLACE) {
-        int nb = P::nat(b * M);
+        const int nb = P::nat(b * M);
 #pragma unroll
         for (int q = 0; q < R; ++q) st(line, nb + q * (P::N / R), v[i][q]);
       } else {
@@ -247,7 +261,7 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
 template <class P, int S0, int S1, bool INV, int LINES, int LS, int PS, int NT>
 __device__ __forceinline__ void dif_stages_smem(float2* sm, const float2* __restrict__ tw, int twmul) {
   if constexpr (S0 < S1) {
-    auto ld = [&](int line, int pos) { return sm[line * LS + pos * PS]; };
+    auto ld = [&](int line, int pos, int, int) { return sm[line * LS + pos * PS]; };
     auto st = [&](int line, int pos, float2 val) { sm[line * LS + pos * PS] = val; };
     dif_stage<P, S0, INV, LINES, NT, OUT_INPLACE>(ld, st, tw, twmul);
     __syncthreads();
@@ -258,7 +272,7 @@ __device__ __forceinline__ void dif_stages_smem(float2* sm, const float2* __rest
 // Last stage with the outputs re-sorted to natural order inside the same buffer.
 template <class P, bool INV, int LINES, int LS, int PS, int NT>
 __device__ __forceinline__ void dif_last_resort_smem(float2* sm, const float2* __restrict__ tw, int twmul) {
-  auto ld = [&](int line, int pos) { return sm[line * LS + pos * PS]; };
+  auto ld = [&](int line, int pos, int, int) { return sm[line * LS + pos * PS]; };
   auto st = [&](int line, int k, float2 val) { sm[line * LS + k * PS] = val; };
   dif_stage<P, P::S - 1, INV, LINES, NT, OUT_RESORT>(ld, st, tw, twmul);
   __syncthreads();
