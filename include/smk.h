@@ -123,6 +123,7 @@ typedef struct smk_geom {
   double dx, dy, dz;    /* cell size */
   double r0;            /* h*R(z0): distance of the box centre */
   int dmax;             /* half width of the Gaussian window in cells (3) */
+  double pixel_step;    /* spacing of rvec in Mpc/h (make_spectra.py -pixel, 0.2); 0 = unknown / non-uniform */
 } smk_geom;
 
 int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs, double xmin,

@@ -23,7 +23,7 @@ class SmkError(RuntimeError):
 
 class Geom(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("dx", C.c_double), ("dy", C.c_double),
-                ("dz", C.c_double), ("r0", C.c_double), ("dmax", C.c_int)]
+                ("dz", C.c_double), ("r0", C.c_double), ("dmax", C.c_int), ("pixel_step", C.c_double)]
 
 
 _lib = None

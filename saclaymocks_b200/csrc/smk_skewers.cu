@@ -7,6 +7,7 @@
 // exp(-|dr|^2 / 2 DX^2) factorise as wx*wy*wz, so 21 exponentials are evaluated per pixel instead
 // of 343; sums run in float32 (|error| ~1e-6 of the field rms, far inside the 1e-5 tolerance on F).
 #include <math.h>
+#include <stdlib.h>
 
 #include "smk_internal.h"
 
@@ -127,12 +128,227 @@ __global__ void __launch_bounds__(128) skewers_kernel(SkewerParams p, int nchunk
   }
 }
 
-int launch_skewers(const SkewerParams& p, int dmax, cudaStream_t st) {
+// ---- register-blocked variant: each thread owns P consecutive pixels of one sightline and walks the UNION of
+// their (2*DMAX+1)^3 windows once, so that every field value loaded is used by P pixels.  P consecutive pixels
+// span (P-1)*pixel < one cell, hence the union is at most one cell wider per axis; a pixel's weight is zero outside
+// its own window, which keeps the result identical to the reference's truncated Gaussian sum.
+template <int DMAX, int P, int NF, bool INTERIOR>
+__device__ __forceinline__ void gather_multi(const SkewerParams& p, const float* const (&fp)[NF], int bx, int by,
+                                             int bz, int nxu, int nyu, const int (&dix)[P], const int (&diy)[P],
+                                             const float (&ox)[P], const float (&oy)[P],
+                                             const float (&wz)[P][2 * DMAX + 2], float inv_sig2, float (&acc)[NF][P],
+                                             float (&sx)[P], float (&sy)[P]) {
+  constexpr int WU = 2 * DMAX + 2;
+  const float fdx = (float)p.dx, fdy = (float)p.dy;
+#pragma unroll
+  for (int f = 0; f < NF; ++f)
+#pragma unroll
+    for (int q = 0; q < P; ++q) acc[f][q] = 0.f;
+  int lz[WU];
+#pragma unroll
+  for (int c = 0; c < WU; ++c) lz[c] = INTERIOR ? c : min(max(bz - DMAX + c, 0), p.nz - 1);
+  const int z0 = INTERIOR ? bz - DMAX : 0;      // INTERIOR: the z window [bz-DMAX, bz+DMAX+1] needs no clamping
+#pragma unroll
+  for (int q = 0; q < P; ++q) { sx[q] = 0.f; sy[q] = 0.f; }
+  const unsigned plane = (unsigned)p.ny * (unsigned)p.nz;
+  for (int a = 0; a < nxu; ++a) {
+    const int la = INTERIOR ? (bx - DMAX + a - p.ix0) : min(max(bx - DMAX + a - p.ix0, 0), p.nxs - 1);
+    float wxa[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      const int m = a - DMAX - dix[q];                      // cell offset from pixel q's own cell
+      const float t = m * fdx + ox[q];
+      wxa[q] = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
+      sx[q] += wxa[q];
+    }
+    for (int b = 0; b < nyu; ++b) {
+      const int lb = INTERIOR ? (by - DMAX + b) : min(max(by - DMAX + b, 0), p.ny - 1);
+      float wab[P];
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        const int m = b - DMAX - diy[q];
+        const float t = m * fdy + oy[q];
+        const float wyb = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
+        if (a == 0) sy[q] += wyb;
+        wab[q] = wxa[q] * wyb;
+      }
+      const size_t row = (size_t)la * plane + (unsigned)lb * (unsigned)p.nz + z0;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const float* __restrict__ src = fp[f] + row;
+        float r[WU];
+#pragma unroll
+        for (int c = 0; c < WU; ++c) r[c] = __ldg(src + lz[c]);
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < WU; ++c) s = fmaf(wz[q][c], r[c], s);
+          acc[f][q] = fmaf(wab[q], s, acc[f][q]);
+        }
+      }
+    }
+  }
+}
+
+template <int DMAX, int P>
+__device__ __forceinline__ void pixel_xyz(const SkewerParams& p, int q, int i, double& xv, double& yv, double& zv) {
+  const double R = p.qso[4 * q + 3], r = p.rvec[i];
+  xv = r * p.qso[4 * q] / R;                 // make_spectra.py:443-452 (same operation order)
+  yv = r * p.qso[4 * q + 1] / R;
+  zv = r * p.qso[4 * q + 2] / R;
+}
+
+template <int DMAX, int P>
+__global__ void __launch_bounds__(128, 3) skewers_multi_kernel(const __grid_constant__ SkewerParams p, int nchunk) {
+  constexpr int WU = 2 * DMAX + 2;
+  const int q = blockIdx.x / nchunk;
+  const int i0 = ((blockIdx.x - q * nchunk) * blockDim.x + threadIdx.x) * P;
+  if (i0 >= p.npix) return;
+  const int nfor = p.npix_forest[q];
+  const double LX = p.dx * p.nx, LY = p.dy * p.ny, LZ = p.dz * p.nz;
+  const float inv_sig2 = (float)(1.0 / (2.0 * p.dx * p.dx));
+  const float fdz = (float)p.dz;
+  unsigned actmask = 0;
+  int ix[P], iy[P], iz[P];
+  float ox[P], oy[P], oz[P];
+  int bx = 1 << 30, by = 1 << 30, bz = 1 << 30, tx = -(1 << 30), ty = -(1 << 30), tz = -(1 << 30);
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const int i = i0 + k;
+    ix[k] = iy[k] = iz[k] = 0;
+    ox[k] = oy[k] = oz[k] = 0.f;
+    if (i >= p.npix) continue;
+    double xv, yv, zv;
+    pixel_xyz<DMAX, P>(p, q, i, xv, yv, zv);
+    if (!(xv > p.xmin) || !(xv <= p.xmax)) continue;            // owned by another slab
+    if (i >= nfor) {                                            // make_spectra.py:99-101
+      const size_t o = (size_t)q * p.npix + i;
+      p.delta_l[o] = -1000000.f;
+      if (p.eta_par) p.eta_par[o] = 0.f;
+      if (p.vpar) p.vpar[o] = 0.f;
+      continue;
+    }
+    ix[k] = (int)((xv + LX / 2) / p.dx);                        // make_spectra.py:47-49
+    iy[k] = (int)((yv + LY / 2) / p.dy);
+    iz[k] = (int)((zv + LZ / 2 - p.r0) / p.dz);
+    ox[k] = (float)((ix[k] + 0.5) * p.dx - LX / 2 - xv);        // cell centre - pixel, make_spectra.py:54-56
+    oy[k] = (float)((iy[k] + 0.5) * p.dy - LY / 2 - yv);
+    oz[k] = (float)((iz[k] + 0.5) * p.dz - LZ / 2 + p.r0 - zv);
+    actmask |= 1u << k;
+    bx = min(bx, ix[k]); by = min(by, iy[k]); bz = min(bz, iz[k]);
+    tx = max(tx, ix[k]); ty = max(ty, iy[k]); tz = max(tz, iz[k]);
+  }
+  if (!actmask) return;
+  // the host guarantees (P-1)*pixel < cell size, so tx-bx, ty-by, tz-bz are 0 or 1
+  const int nxu = 2 * DMAX + 1 + (tx - bx), nyu = 2 * DMAX + 1 + (ty - by);
+  int dix[P], diy[P];
+  float wz[P][WU], sz[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const bool act = (actmask >> k) & 1;
+    dix[k] = act ? ix[k] - bx : 100;      // an inactive pixel gets zero weight everywhere
+    diy[k] = iy[k] - by;
+    sz[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < WU; ++c) {
+      const int m = c - DMAX - (iz[k] - bz);
+      const float t = m * fdz + oz[k];
+      wz[k][c] = (act && m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
+      sz[k] += wz[k][c];
+    }
+  }
+  // whole union window inside the slab: no index clamping, z offsets become immediates
+  const bool interior = bx - DMAX - p.ix0 >= 0 && bx - DMAX - p.ix0 + nxu <= p.nxs && by - DMAX >= 0 &&
+                        by - DMAX + nyu <= p.ny && bz - DMAX >= 0 && bz + DMAX + 1 < p.nz;
+  float sx[P], sy[P];
+  const int NFI = p.rsd ? (p.dla ? 10 : 7) : 1;
+  float d0[P], inv_sw[P];
+  double eta[P], vel[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) { eta[k] = 0.0; vel[k] = 0.0; }
+#define SMK_GATHER(NF_, ACC, SX, SY)                                                                              \
+  if (interior) gather_multi<DMAX, P, NF_, true>(p, fp, bx, by, bz, nxu, nyu, dix, diy, ox, oy, wz, inv_sig2, ACC, SX, SY); \
+  else gather_multi<DMAX, P, NF_, false>(p, fp, bx, by, bz, nxu, nyu, dix, diy, ox, oy, wz, inv_sig2, ACC, SX, SY);
+  if (NFI == 1) {
+    float acc[1][P];
+    const float* const fp[1] = {p.f[0]};
+    SMK_GATHER(1, acc, sx, sy)
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      inv_sw[k] = ((actmask >> k) & 1) ? 1.0f / (sx[k] * sy[k] * sz[k]) : 0.f;
+      d0[k] = acc[0][k];
+    }
+  } else {
+    {   // group A: delta, eta_xx, eta_yy, eta_zz, eta_xy
+      float acc[5][P];
+      const float* const fp[5] = {p.f[0], p.f[1], p.f[2], p.f[3], p.f[4]};
+      SMK_GATHER(5, acc, sx, sy)
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        inv_sw[k] = ((actmask >> k) & 1) ? 1.0f / (sx[k] * sy[k] * sz[k]) : 0.f;
+        d0[k] = acc[0][k];
+        double xv, yv, zv;
+        pixel_xyz<DMAX, P>(p, q, min(i0 + k, p.npix - 1), xv, yv, zv);
+        eta[k] = xv * (double)(acc[1][k] * inv_sw[k]) * xv + yv * (double)(acc[2][k] * inv_sw[k]) * yv +
+                 zv * (double)(acc[3][k] * inv_sw[k]) * zv + 2 * xv * (double)(acc[4][k] * inv_sw[k]) * yv;
+      }
+    }
+    float sx2[P], sy2[P];
+    if (NFI == 10) {   // group B: eta_xz, eta_yz, vx, vy, vz
+      float acc[5][P];
+      const float* const fp[5] = {p.f[5], p.f[6], p.f[7], p.f[8], p.f[9]};
+      SMK_GATHER(5, acc, sx2, sy2)
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        double xv, yv, zv;
+        pixel_xyz<DMAX, P>(p, q, min(i0 + k, p.npix - 1), xv, yv, zv);
+        eta[k] += 2 * xv * (double)(acc[0][k] * inv_sw[k]) * zv + 2 * yv * (double)(acc[1][k] * inv_sw[k]) * zv;
+        vel[k] = (double)(acc[2][k] * inv_sw[k]) * xv + (double)(acc[3][k] * inv_sw[k]) * yv +
+                 (double)(acc[4][k] * inv_sw[k]) * zv;
+      }
+    } else {           // group B': eta_xz, eta_yz
+      float acc[2][P];
+      const float* const fp[2] = {p.f[5], p.f[6]};
+      SMK_GATHER(2, acc, sx2, sy2)
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        double xv, yv, zv;
+        pixel_xyz<DMAX, P>(p, q, min(i0 + k, p.npix - 1), xv, yv, zv);
+        eta[k] += 2 * xv * (double)(acc[0][k] * inv_sw[k]) * zv + 2 * yv * (double)(acc[1][k] * inv_sw[k]) * zv;
+      }
+    }
+  }
+#undef SMK_GATHER
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    if (!((actmask >> k) & 1)) continue;
+    const size_t o = (size_t)q * p.npix + i0 + k;
+    double xv, yv, zv;
+    pixel_xyz<DMAX, P>(p, q, i0 + k, xv, yv, zv);
+    const double RR = xv * xv + yv * yv + zv * zv;
+    p.delta_l[o] = d0[k] * inv_sw[k];
+    if (p.eta_par) p.eta_par[o] = NFI >= 7 ? (float)(eta[k] / RR) : 0.f;
+    if (p.vpar) p.vpar[o] = NFI == 10 ? (float)(vel[k] / sqrt(RR)) : 0.f;
+  }
+}
+
+int launch_skewers(const SkewerParams& p, int dmax, double pixel_step, cudaStream_t st) {
   if (p.nqso == 0 || p.npix == 0) return SMK_OK;
   const int NT = 128;
-  int nchunk = (p.npix + NT - 1) / NT;
+  // register-blocked kernel: valid while P consecutive pixels cannot cross two cell boundaries on any axis
+  constexpr int PB = 4;
+  const double cell = fmin(p.dx, fmin(p.dy, p.dz));
+  const bool multi = (dmax == 3) && pixel_step > 0 && (PB - 1) * pixel_step < cell;
+  int per_block = multi ? NT * PB : NT;
+  int nchunk = (p.npix + per_block - 1) / per_block;
   long long nblocks = (long long)nchunk * p.nqso;
   if (nblocks > 2147483647LL) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
+  if (multi) {
+    skewers_multi_kernel<3, PB><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk);
+    SMK_CUDA_OK(cudaGetLastError());
+    return SMK_OK;
+  }
   switch (dmax) {
     case 1: skewers_kernel<1><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk); break;
     case 2: skewers_kernel<2><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk); break;
@@ -172,5 +388,10 @@ extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const f
   p.nqso = nqso; p.npix = npix;
   p.qso = qso_xyzr; p.npix_forest = npix_forest; p.rvec = rvec;
   p.delta_l = delta_l; p.eta_par = eta_par; p.vpar = vpar;
-  return launch_skewers(p, g->dmax, smk_ctx_stream(ctx));
+  // largest step between consecutive pixels of the grid (uniform 0.2 Mpc/h in the reference); decides whether the
+  // register-blocked kernel may be used.  SMK_SKEWERS_SIMPLE=1 forces the one-pixel-per-thread kernel.
+  double step = g->pixel_step;
+  const char* env = getenv("SMK_SKEWERS_SIMPLE");
+  if (env && env[0] == '1') step = 0.0;
+  return launch_skewers(p, g->dmax, step, smk_ctx_stream(ctx));
 }

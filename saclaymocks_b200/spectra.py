@@ -51,7 +51,7 @@ class SkewerGeometry(object):
                 * cosmo_mod.lin_interp(self._dg[0], self._dg[1], z) / self.dgrowth0)
 
     def c_geom(self):
-        return _lib.Geom(self.NX, self.NY, self.NZ, self.DX, self.DY, self.DZ, self.R0, self.dmax)
+        return _lib.Geom(self.NX, self.NY, self.NZ, self.DX, self.DY, self.DZ, self.R0, self.dmax, self.pixel)
 
 
 def qso_lines_of_sight(geom, ra, dec, zqso, ra0, dec0):

@@ -192,3 +192,21 @@ def test_smallscale_and_fgpa_vs_oracle(cuda):
                       fg.b.cpu().numpy().astype(np.float64), fg.c.cpu().numpy().astype(np.float64))
         assert np.max(np.abs(F - ref)) < 1e-5
         assert np.all(F[:, -100:] == 1.0)
+
+
+def test_register_blocked_kernel_equals_simple_kernel(cuda, golden_ref32, monkeypatch):
+    """The P-pixels-per-thread gather (union window) against the one-pixel-per-thread kernel on the same input."""
+    from saclaymocks_b200 import spectra as sp
+    g = golden_ref32
+    rng = np.random.default_rng(3)
+    boxes = {k: rng.standard_normal((32, 32, 1536), dtype=np.float32) for k in sp.FIELDS}
+    monkeypatch.setenv("SMK_SKEWERS_SIMPLE", "1")
+    _, _, _, _, simple = _gpu_skewers(g, boxes, cuda, slabs=2)
+    monkeypatch.delenv("SMK_SKEWERS_SIMPLE")
+    _, _, _, _, multi = _gpu_skewers(g, boxes, cuda, slabs=2)
+    for a, b, tol in zip(simple, multi, (3e-6, 3e-6, 3e-6)):
+        a, b = a.cpu().numpy(), b.cpu().numpy()
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        m = ~np.isnan(a)
+        assert m.sum() > 10000
+        assert np.max(np.abs(a[m] - b[m])) < tol
