@@ -1,0 +1,101 @@
+"""Multi-GPU parity: the x-slab / y-slab sharded pipeline (all-to-all transposes, halo exchange, skewers sharded by
+owning slab) against the CPU oracle.  Needs >= 2 GPUs (skipped otherwise): run with `gpurun --gpus 2`."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _worker(rank, world, port, shape, dcell, out):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from oracle import boxes as ob
+    from oracle import pk_weights
+    from oracle import spectra as osp
+    from saclaymocks_b200.chunk import ChunkPipeline
+    from saclaymocks_b200 import spectra as sp
+    from helpers import rel_l2
+    NX, NY, NZ = shape
+    W = pk_weights.weights(NX, NY, NZ, dcell)
+    noise = ob.draw_noise(NX, NY, NZ, 42)
+    raw, p0, boxes, sig = ob.make_boxes(NX, NY, NZ, dcell, 42, W, noise=noise)
+    pipe = ChunkPipeline(NX, NY, NZ, dcell, device=dev, rank=rank, nranks=world, zfix=2.4)
+    nyl, nxl = NY // world, NX // world
+    pipe.set_weights({k: v[:, rank * nyl:(rank + 1) * nyl] for k, v in W.items()})
+    # synthetic quasars inside the box
+    rng = np.random.default_rng(5)
+    geom = pipe.geom
+    half = np.degrees(np.arctan((geom.LX / 2 - 3 * dcell) / (geom.R0 + geom.LZ / 2))) * 0.95
+    nq = 24
+    ra = (190.0 + rng.uniform(-half, half, nq)).astype("f4")
+    dec = (0.0 + rng.uniform(-half, half, nq)).astype("f4")
+    z = rng.uniform(2.0, 3.5, nq).astype("f4")
+    pipe.set_catalogue(ra, dec, z, 190.0, 0.0)
+    pipe.step_boxes(noise=torch.as_tensor(noise[rank * nxl:(rank + 1) * nxl].copy(), device=dev))
+    errs = {}
+    for name in ob.PRODUCTS:
+        got = pipe.interior(name).cpu().numpy()
+        errs[name] = rel_l2(got, boxes[name][rank * nxl:(rank + 1) * nxl])
+    sg = pipe.sigmas()
+    errs["sigma"] = max(abs(sg[n] / sig[n] - 1) for n in ob.PRODUCTS)
+    # skewers: every rank computes the pixels its slab owns; compare with the oracle's per-slab pieces
+    dl, ep, vp, F = (t.cpu().numpy() for t in pipe.step_skewers())
+    og = osp.Geometry(NX, NY, NZ, dcell)
+    q = np.zeros(nq, dtype=[("RA", "f4"), ("DEC", "f4"), ("Z_QSO_NO_RSD", "f4"), ("Z_QSO_RSD", "f4"),
+                            ("THING_ID", "i8"), ("HDU", "i4")])
+    q["RA"], q["DEC"], q["Z_QSO_RSD"], q["Z_QSO_NO_RSD"], q["THING_ID"] = ra, dec, z, z, np.arange(nq)
+    files = [q] * world            # every "file" holds the whole catalogue: the half-selection then keeps all of it
+    lam32 = np.float32(geom.lambda_vec)
+    worst = 0.0
+    npieces = 0
+    sel = list(pipe.cat["sel"])
+    for p in osp.make_spectra_slice(og, boxes, [q[:0]] * (world // 2) + [q] + [q[:0]] * (world - world // 2 - 1)
+                                    if rank >= world // 2 else [q] + [q[:0]] * (world - 1), rank, world, 190.0, 0.0):
+        idx = np.searchsorted(lam32, p["lam"])
+        row = sel.index(p["id"])
+        m = p["delta_l"] > -1e5
+        worst = max(worst, float(np.max(np.abs(dl[row, idx][m] - p["delta_l"][m]))) if m.any() else 0.0,
+                    float(np.max(np.abs(ep[row, idx] - p["eta_par"]))))
+        assert np.all(dl[row, idx][~m] == -1e6)
+        npieces += 1
+    errs["skewers"] = worst
+    errs["npieces"] = npieces
+    import json
+    json.dump({k: float(v) for k, v in errs.items()}, open(out + ".%d" % rank, "w"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (32, 32, 96)), (2, (64, 32, 96)), (4, (64, 64, 96))])
+def test_sharded_pipeline_matches_oracle(tmp_path, world, shape):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res")
+    port = 29600 + world + shape[0]
+    mp.spawn(_worker, args=(world, port, shape, 3364.0 / shape[2], out), nprocs=world, join=True)
+    pieces = 0
+    for r in range(world):
+        import json
+        errs = json.load(open(out + ".%d" % r))
+        for k, v in errs.items():
+            if k == "npieces":
+                pieces += v
+            elif k == "skewers":
+                assert v < 1e-5, (r, k, v)
+            elif k == "sigma":
+                assert v < 1e-4, (r, k, v)
+            else:
+                assert v < 1e-5, (r, k, v)
+    assert pieces > 0
