@@ -77,30 +77,43 @@ def weight_tables_device(bs, device):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled through NVML every 20 ms while the timed region runs."""
+
     def __init__(self, gpu_index=0):
         self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
         self.idx = gpu_index
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self._stop.wait(0.02)
+        except Exception as e:          # NVML missing: fall back to one nvidia-smi query
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(o[0]))
-                self.max_mhz = float(o[1])
-                for nm, v in zip(names, o[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nm)
+                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=clocks.sm,clocks.max.sm",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                v = o.stdout.strip().split(",")
+                self.samples.append(float(v[0]))
+                self.max_mhz = float(v[1])
             except Exception:
-                pass
-            self._stop.wait(0.2)
+                self.reasons.add("clock query failed: %s" % e)
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):

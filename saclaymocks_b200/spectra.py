@@ -117,13 +117,17 @@ class FGPA(object):
         self.geom = geom
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.pixsize = pixsize
-        z = np.full(geom.npixeltot, zfix, dtype=np.float64) if zfix else geom.redshift.copy()
-        self.z = z
+        # merge_spectra.py:285-288: z is FLOAT32 in both modes (zfix * ones_like(float32 LAMBDA), or the float32
+        # REDSHIFT HDU).  Kept: with -zfix 2.4 the float32 value 2.4000001 and the float32 pairwise mean of the forest
+        # decide the tie between the tabulated P1D_miss redshifts 2.2 and 2.6.
+        z32 = np.full(geom.npixeltot, zfix, dtype=np.float32) if zfix else np.float32(geom.redshift)
+        self.z = z32
+        z = z32.astype(np.float64)
         pz, pa, pb, pc = tables.params(paramfile)
         a = cosmo_mod.lin_interp(pz, pa, z) if aa <= 0 else np.full_like(z, aa)
         b = cosmo_mod.lin_interp(pz, pb, z) if bb <= 0 else np.full_like(z, bb)
         c = cosmo_mod.lin_interp(pz, pc, z) if cc <= 0 else np.full_like(z, cc)
-        growthf = cosmo_mod.fgrowth(2.4, constant.omega_M_0) * (1 + 2.4) / (1 + z)     # merge_spectra.py:296
+        growthf = cosmo_mod.fgrowth(2.4, constant.omega_M_0) * (1 + 2.4) / (1 + z32)   # merge_spectra.py:296 (float32)
         self.growthf = growthf
         f32 = lambda v: torch.as_tensor(np.float32(v), device=self.device)
         self.a, self.b, self.c, self.G = f32(a), f32(b), f32(c), f32(growthf)
