@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import slab
 from . import spectra as sp
 from .boxes import BoxSynth, PRODUCTS, WEIGHT_OF
 
@@ -30,8 +31,7 @@ class ChunkPipeline(object):
         bs = self.bs
         self.boxk = bs.empty_boxk()
         # halo'd slabs: [halo_lo + nxl + halo_hi, NY, NZ]; global edges get no halo (make_spectra.py:220-221)
-        self.hlo = dmax if rank > 0 else 0
-        self.hhi = dmax if rank < nranks - 1 else 0
+        self.hlo, self.hhi = slab.halo(rank, nranks, dmax)
         self.plane = bs.NY * bs.NZ
         self.fields = {}
         for name in PRODUCTS:
@@ -56,12 +56,8 @@ class ChunkPipeline(object):
         g = self.geom
         xyzr, nfor = sp.qso_lines_of_sight(g, ra, dec, z, ra0, dec0)
         keep = nfor >= 0
-        xmin = g.LX * self.rank / self.nranks - g.LX / 2
-        xmax = g.LX * (self.rank + 1) / self.nranks - g.LX / 2
-        # sightline X runs monotonically from X*Rmin/R to X*Rmax_forest/R: keep quasars that can touch the slab
-        xa = xyzr[:, 0] * g.R_vec[0] / xyzr[:, 3]
-        xb = xyzr[:, 0] * g.R_vec[-1] / xyzr[:, 3]
-        touch = (np.minimum(xa, xb) <= xmax) & (np.maximum(xa, xb) > xmin)
+        xmin, xmax = slab.x_bounds(self.rank, self.nranks, g.LX)
+        touch = slab.touching(xyzr, g.R_vec[0], g.R_vec[-1], xmin, xmax)
         sel = np.where(keep & touch)[0]
         ids = np.arange(len(nfor), dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
         self.cat = dict(sel=sel, xyzr=np.ascontiguousarray(xyzr[sel]), nfor=np.ascontiguousarray(nfor[sel]),
