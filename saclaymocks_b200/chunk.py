@@ -39,9 +39,11 @@ class ChunkPipeline(object):
             self.fields[name] = torch.empty((bs.nxl + h, bs.NY, bs.NZ), dtype=torch.float32, device=device)
         self.stats = torch.zeros((len(PRODUCTS), 2), dtype=torch.float64, device=device)
         if nranks > 1:
+            # two exchange buffer pairs: the all-to-all of product p overlaps the x pass of p+1 and the y/z passes of p-1
             n = bs.NX * bs.nyl * bs.pitch
-            self.sendbuf = torch.empty(n, dtype=torch.complex64, device=device)
-            self.recvbuf = torch.empty(n, dtype=torch.complex64, device=device)
+            self.sendbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
+            self.recvbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
+            self.sendbuf, self.recvbuf = self.sendbufs[0], self.recvbufs[0]
         self.W = None
         self.cat = None
         # kernels per step: 3 forward passes + 13 x 3 inverse passes + gather + small-scale + FGPA
@@ -119,8 +121,32 @@ class ChunkPipeline(object):
     def step_boxes(self, seed=0, noise=None, products=PRODUCTS):
         self.stats.zero_()
         self.forward(seed, noise)
-        for name in products:
-            self.product(name)
+        if self.nranks == 1:
+            for name in products:
+                self.product(name)
+            return
+        # software pipeline over the independent inverse transforms (boxk is read-only after the 'box' product has
+        # stored boxk*P0 back, and the products before it only read it): x pass of p | all-to-all of p-1 | y,z of p-2
+        bs, L = self.bs, self.bs.lib
+        pending = None            # (work, slot, name)
+        for i, name in enumerate(products):
+            slot = i & 1
+            pid = _lib.PRODUCT_ID[name]
+            wt = self.W[WEIGHT_OF[name]] if name in WEIGHT_OF else None
+            _lib.check(L.smk_synth_c2r_local(bs.h, _ptr(self.boxk), pid, _ptr(wt), 1, C.c_double(bs.dgrowth0),
+                                             _ptr(self.sendbufs[slot])))
+            work = torch.distributed.all_to_all_single(self.recvbufs[slot], self.sendbufs[slot], group=self.group,
+                                                       async_op=True)
+            if pending is not None:
+                self._finish(*pending)
+            pending = (work, slot, name)
+        self._finish(*pending)
+
+    def _finish(self, work, slot, name):
+        work.wait()               # the compute stream waits for the exchange; the host does not block
+        pid = _lib.PRODUCT_ID[name]
+        _lib.check(self.bs.lib.smk_synth_c2r_finish(self.bs.h, _ptr(self.recvbufs[slot]), _ptr(self.interior(name)),
+                                                    _ptr(self.stats[pid])))
 
     def sigmas(self):
         """np.std of every product over the whole box (all ranks)."""

@@ -90,12 +90,12 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT) c2c_strided_kernel(const
     const float ka = p.mul.fa == 0 ? kx : (p.mul.fa == 1 ? ky : kz);
     if (MUL == MUL_ETA) {
       const float kb = p.mul.fb == 0 ? kx : (p.mul.fb == 1 ? ky : kz);
-      const float f = __fdiv_rn(__fmul_rn(ka, kb), kk);
+      const float f = fdiv_fast(__fmul_rn(ka, kb), kk, rcp_approx(kk));
       return make_float2(__fmul_rn(v.x, f), __fmul_rn(v.y, f));
     }
     // MUL_VEL: boxk *= -1j*k/kk*H0*dgrowth0 -- float32 up to "*H0", then float64 (numpy promotes on the float64
     // scalar dgrowth0 and rounds the complex128 product back to complex64)
-    const float f32 = __fmul_rn(__fdiv_rn(-ka, kk), 100.0f);
+    const float f32 = __fmul_rn(fdiv_fast(-ka, kk, rcp_approx(kk)), 100.0f);
     const double f = (double)f32 * p.mul.vscale;
     return make_float2((float)(-(double)v.y * f), (float)((double)v.x * f));
   };
@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
   dif_last_resort_smem<P, true, LINES, LP, 1, NT>(sm, p.tw, 2);
   // ---- store x[2n], x[2n+1] = z[n] / N, accumulate sum and sum of squares
   float s1 = 0.f, s2 = 0.f;
+  const float rnorm = __frcp_rn(p.norm);
   float2* out2 = reinterpret_cast<float2*>(p.out);
   for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
     if (line0 + line < p.nlines) {
@@ -299,8 +300,8 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
 #pragma unroll 8
       for (int n = threadIdx.x & 31; n < M; n += 32) {
         float2 z = sm[line * LP + n];
-        z.x = __fdiv_rn(z.x, p.norm);
-        z.y = __fdiv_rn(z.y, p.norm);
+        z.x = fdiv_fast(z.x, p.norm, rnorm);
+        z.y = fdiv_fast(z.y, p.norm, rnorm);
         dst[n] = z;
         s1 += z.x + z.y;
         s2 += z.x * z.x + z.y * z.y;
