@@ -11,6 +11,13 @@
 
 #include "smk_internal.h"
 
+#ifndef SMK_SKEW_P
+#define SMK_SKEW_P 4
+#endif
+#ifndef SMK_SKEW_MINB
+#define SMK_SKEW_MINB 3
+#endif
+
 namespace smk {
 
 struct SkewerParams {
@@ -199,8 +206,8 @@ __device__ __forceinline__ void pixel_xyz(const SkewerParams& p, int q, int i, d
   zv = r * p.qso[4 * q + 2] / R;
 }
 
-template <int DMAX, int P>
-__global__ void __launch_bounds__(128, 3) skewers_multi_kernel(const __grid_constant__ SkewerParams p, int nchunk) {
+template <int DMAX, int P, int MINB>
+__global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_constant__ SkewerParams p, int nchunk) {
   constexpr int WU = 2 * DMAX + 2;
   const int q = blockIdx.x / nchunk;
   const int i0 = ((blockIdx.x - q * nchunk) * blockDim.x + threadIdx.x) * P;
@@ -333,22 +340,38 @@ __global__ void __launch_bounds__(128, 3) skewers_multi_kernel(const __grid_cons
   }
 }
 
+template <int P, int MINB>
+static int launch_multi(const SkewerParams& p, cudaStream_t st) {
+  const int NT = 128;
+  int nchunk = (p.npix + NT * P - 1) / (NT * P);
+  long long nblocks = (long long)nchunk * p.nqso;
+  if (nblocks > 2147483647LL) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
+  skewers_multi_kernel<3, P, MINB><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk);
+  SMK_CUDA_OK(cudaGetLastError());
+  return SMK_OK;
+}
+
 int launch_skewers(const SkewerParams& p, int dmax, double pixel_step, cudaStream_t st) {
   if (p.nqso == 0 || p.npix == 0) return SMK_OK;
   const int NT = 128;
   // register-blocked kernel: valid while P consecutive pixels cannot cross two cell boundaries on any axis
-  constexpr int PB = 4;
   const double cell = fmin(p.dx, fmin(p.dy, p.dz));
+  int variant = SMK_SKEW_P;
+  const char* env = getenv("SMK_SKEW_VARIANT");      // tuning knob: pixels per thread (2, 3, 4) or 44 (4 px, 4 CTAs/SM)
+  if (env) variant = atoi(env);
+  const int PB = variant == 44 ? 4 : variant;
   const bool multi = (dmax == 3) && pixel_step > 0 && (PB - 1) * pixel_step < cell;
-  int per_block = multi ? NT * PB : NT;
-  int nchunk = (p.npix + per_block - 1) / per_block;
+  if (multi) {
+    switch (variant) {
+      case 2: return launch_multi<2, 5>(p, st);
+      case 3: return launch_multi<3, 4>(p, st);
+      case 44: return launch_multi<4, 4>(p, st);
+      default: return launch_multi<4, 3>(p, st);
+    }
+  }
+  int nchunk = (p.npix + NT - 1) / NT;
   long long nblocks = (long long)nchunk * p.nqso;
   if (nblocks > 2147483647LL) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
-  if (multi) {
-    skewers_multi_kernel<3, PB><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk);
-    SMK_CUDA_OK(cudaGetLastError());
-    return SMK_OK;
-  }
   switch (dmax) {
     case 1: skewers_kernel<1><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk); break;
     case 2: skewers_kernel<2><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk); break;
