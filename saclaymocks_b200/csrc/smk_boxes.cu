@@ -220,29 +220,25 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
   // ---- M-point complex FFT of z[n] = x[2n] + i x[2n+1], output re-sorted to natural order
   dif_stages_smem<P, 0, P::S - 1, false, LINES, LP, 1, NT>(sm, p.tw, 2);
   dif_last_resort_smem<P, false, LINES, LP, 1, NT>(sm, p.tw, 2);
-  // ---- X[k] = (Z[k]+conj(Z[M-k]))/2 - (i/2) w^k (Z[k]-conj(Z[M-k])),  k = 0..M  (pairs k, M-k in place)
-  for (int task = threadIdx.x; task < LINES * (M / 2 + 1); task += NT) {
-    int line = task % LINES, k = task / LINES;
-    float2* row = sm + line * LP;
-    float2 a = row[k], b = (k == 0) ? a : row[M - k];
-    float2 w = __ldg(p.tw + k);                       // exp(-2 pi i k / NZ)
-    float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));   // (a + conj b)/2
-    float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));   // (a - conj b)/2
-    float2 t = cmul(w, d);
-    float2 mit = make_float2(t.y, -t.x);              // -i t
-    float2 xk = cadd(e, mit);
-    // X[M-k] = conj(e) - (-i conj(w)... ) : derived from the same e, d:  conj(e) + conj(-i t)... = conj(e) - conj(mit)
-    float2 xm = make_float2(e.x - mit.x, -e.y + mit.y);
-    row[k] = xk;
-    if (k != M - k) row[M - k] = xm;
-  }
-  __syncthreads();
-  // ---- store M+1 complex per line (row pads are zeroed so that later passes may stream whole rows)
+  // ---- store with the real-transform post-step fused in: X[k] = (Z[k]+conj(Z[M-k]))/2 - (i/2) w^k (Z[k]-conj(Z[M-k]))
+  //      for the pair (k, M-k); one warp per line, both global writes coalesced; row pads are zeroed so that later
+  //      passes may stream whole rows
   for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
     if (line0 + line < p.nlines) {
+      const float2* row = sm + line * LP;
       float2* dst = p.out + (line0 + line) * p.pitch;
-#pragma unroll 8
-      for (int k = threadIdx.x & 31; k < p.pitch; k += 32) dst[k] = (k <= M) ? sm[line * LP + k] : make_float2(0.f, 0.f);
+#pragma unroll 4
+      for (int k = threadIdx.x & 31; k <= M / 2; k += 32) {
+        float2 a = row[k], b = (k == 0) ? a : row[M - k];
+        float2 w = __ldg(p.tw + k);                       // exp(-2 pi i k / NZ)
+        float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));   // (a + conj b)/2
+        float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));   // (a - conj b)/2
+        float2 t = cmul(w, d);
+        float2 mit = make_float2(t.y, -t.x);              // -i t
+        dst[k] = cadd(e, mit);
+        if (k != M - k) dst[M - k] = make_float2(e.x - mit.x, -e.y + mit.y);
+      }
+      for (int k = M + 1 + (threadIdx.x & 31); k < p.pitch; k += 32) dst[k] = make_float2(0.f, 0.f);
     }
   }
 }
@@ -264,28 +260,26 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
   extern __shared__ float2 sm[];
   __shared__ double red[2][NT / 32];
   const long long line0 = (long long)blockIdx.x * LINES;
-  for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {        // one warp per line: no index division
+  // ---- load with the real-transform pre-step fused in: one warp per line reads X[k] (ascending) and X[M-k]
+  //      (descending), both coalesced, and writes Z[k] = A + iB, Z[M-k] = conj(A) + i conj(B) with
+  //      A = X[k] + conj(X[M-k]), B = (X[k] - conj(X[M-k])) w^-k.  The imaginary parts of the DC and Nyquist bins
+  //      are ignored, as FFTW's / pocketfft's c2r do.
+  for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
     const bool ok = line0 + line < p.nlines;
     const float2* src = p.in + (line0 + line) * p.pitch;
-#pragma unroll 8
-    for (int k = threadIdx.x & 31; k <= M; k += 32) sm[line * LP + k] = ok ? __ldg(src + k) : make_float2(0.f, 0.f);
-  }
-  __syncthreads();
-  // ---- Z[k] = A + iB, A = X[k] + conj(X[M-k]), B = (X[k] - conj(X[M-k])) w^-k ; imaginary parts of the
-  //      DC and Nyquist bins are ignored, as FFTW's / pocketfft's c2r do
-  for (int task = threadIdx.x; task < LINES * (M / 2 + 1); task += NT) {
-    int line = task % LINES, k = task / LINES;
     float2* row = sm + line * LP;
-    float2 a = row[k], b = row[M - k];
-    if (k == 0) { a.y = 0.f; b.y = 0.f; }
-    float2 w = __ldg(p.tw + k);
-    w.y = -w.y;                                        // exp(+2 pi i k / NZ)
-    float2 A = make_float2(a.x + b.x, a.y - b.y);
-    float2 B = cmul(make_float2(a.x - b.x, a.y + b.y), w);
-    float2 zk = make_float2(A.x - B.y, A.y + B.x);     // A + iB
-    float2 zm = make_float2(A.x + B.y, -A.y + B.x);    // conj(A) + i conj(B)
-    row[k] = zk;
-    if (k != 0 && k != M - k) row[M - k] = zm;
+#pragma unroll 4
+    for (int k = threadIdx.x & 31; k <= M / 2; k += 32) {
+      float2 a = make_float2(0.f, 0.f), b = a;
+      if (ok) { a = __ldg(src + k); b = __ldg(src + M - k); }
+      if (k == 0) { a.y = 0.f; b.y = 0.f; }
+      float2 w = __ldg(p.tw + k);
+      w.y = -w.y;                                        // exp(+2 pi i k / NZ)
+      float2 A = make_float2(a.x + b.x, a.y - b.y);
+      float2 B = cmul(make_float2(a.x - b.x, a.y + b.y), w);
+      row[k] = make_float2(A.x - B.y, A.y + B.x);        // A + iB
+      if (k != 0 && k != M - k) row[M - k] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
+    }
   }
   __syncthreads();
   dif_stages_smem<P, 0, P::S - 1, true, LINES, LP, 1, NT>(sm, p.tw, 2);
