@@ -24,6 +24,10 @@ struct StridedTraits {
   static constexpr int LINES = (N > 1024) ? 8 : 16;
   static constexpr int NT_ = LINES * N / 32;
   static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
+  // resident CTAs per SM the register allocation should allow (shared memory: N*LINES*8 B per CTA)
+  static constexpr int SMEM = N * LINES * 8;
+  static constexpr int MINB_ = 220 * 1024 / SMEM;
+  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ * NT > 1536 ? 1536 / NT : MINB_);
 };
 
 struct StridedParams {
@@ -46,7 +50,10 @@ __device__ __forceinline__ long long point_off(const PassAddr& a, int n) {
 }
 
 template <int N, bool INV, int MUL, bool SPLIT_IN, bool SPLIT_OUT>
-__global__ void __launch_bounds__(StridedTraits<N>::NT) c2c_strided_kernel(const __grid_constant__ StridedParams p) {
+__global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || StridedTraits<N>::MINB == 1)
+                                                              ? StridedTraits<N>::MINB
+                                                              : StridedTraits<N>::MINB - 1)
+    c2c_strided_kernel(const __grid_constant__ StridedParams p) {
   using P = typename PlanFor<N>::type;
   constexpr int LINES = StridedTraits<N>::LINES;
   constexpr int NT = StridedTraits<N>::NT;
