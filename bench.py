@@ -294,8 +294,16 @@ def run_gpu(args):
     per = {k: (ms / n if n else 0.0) for k, (ms, n) in passes.items()}
     dom = max(("inv_x", "inv_y", "c2r_z"), key=lambda k: per[k])
     achieved = alg[dom] / (per[dom] * 1e-3) / 1e9 if per[dom] else 0.0
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (512 x 512 x 1536 only)
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.isfile(tfile) and (nx, ny, world) == (512, 512, 1):
+        tj = json.load(open(tfile))
+        key = {"c2r_z": "c2r_z_kernel<768>", "inv_y": "c2c_strided_kernel<512, 1, 0, 0, 0>",
+               "inv_x": "c2c_strided_kernel<512, 1, 1, 0, 0>"}[dom]
+        traffic = tj.get(key)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": how,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                 "passes_ms": per, "passes_gbs": {k: (alg[k] / (per[k] * 1e-3) / 1e9 if per[k] else None) for k in per},
                 "chunk_gbs": (332.0 * cells / world) / (t_box * 1e-3) / 1e9}
 
