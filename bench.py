@@ -309,7 +309,7 @@ def run_gpu(args):
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU baseline is reported at N=1 only
             cores = os.cpu_count()
             r = cpu_oracle_step(256, cores)
             cpu = {"value": r["value"], "unit": "cells/s", "cores": cores, "kind": "port",

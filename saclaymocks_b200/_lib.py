@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmk.so")
+LIB_PATH = os.environ.get("SMK_LIB_PATH", os.path.join(_HERE, "libsmk.so"))   # override: kernel-variant experiments
 
 NPRODUCTS = 13
 PRODUCT_NAMES = ("boxln_1", "boxln_2", "boxln_3", "box", "eta_xx", "eta_yy", "eta_zz", "eta_xy", "eta_xz", "eta_yz",

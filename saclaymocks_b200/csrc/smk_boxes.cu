@@ -16,14 +16,22 @@
 #include "smk_internal.h"
 #include "smk_philox.cuh"
 
+#ifndef SMK_MID_LINES
+#define SMK_MID_LINES 16  // kz columns per tile for x/y lengths 512 and 1024
+#endif
+#ifndef SMK_BIG_LINES
+#define SMK_BIG_LINES 8   // kz columns per tile for x/y lengths above 1024 (shared memory: N * LINES * 8 B)
+#endif
+
 namespace smk {
 
 // ------------------------------------------------------------------ strided complex pass
 template <int N>
 struct StridedTraits {
-  static constexpr int LINES = (N > 1024) ? 8 : 16;
+  static constexpr int LINES = (N > 1024) ? SMK_BIG_LINES : (N >= 512 ? SMK_MID_LINES : 16);
   static constexpr int NT_ = LINES * N / 32;
-  static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
+  // 2560 = 16*16*2*5: 640 threads give 2 radix-16 butterflies per thread and stage (64 + 32 registers of payload)
+  static constexpr int NT = (N == 2560) ? 640 : (NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_));
   // resident CTAs per SM the register allocation should allow (shared memory: N*LINES*8 B per CTA)
   static constexpr int SMEM = N * LINES * 8;
   static constexpr int MINB_ = 220 * 1024 / SMEM;
@@ -44,7 +52,7 @@ struct StridedParams {
 template <bool SPLIT>
 __device__ __forceinline__ long long point_off(const PassAddr& a, int n) {
   if (!SPLIT) return (long long)n * a.lo_stride;
-  int hi = n / a.nsplit;
+  int hi = a.nsplit >= 2 ? (int)__umulhi((unsigned)n, a.magic) : n;   // n / nsplit, see make_fastdiv()
   int lo = n - hi * a.nsplit;
   return hi * a.hi_stride + lo * a.lo_stride;
 }
@@ -166,6 +174,8 @@ bool strided_size_supported(int n) {
 
 int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, float2* out, PassAddr ain, PassAddr aout,
                        int nouter, int ncols, int wcols, const MulArgs& mul, const float2* tw, cudaStream_t st) {
+  make_fastdiv(ain);
+  make_fastdiv(aout);
   StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw};
   switch (N) {
 #define X(N_) case N_: return launch_strided_n<N_>(inverse, mul_mode, p, nouter, st);

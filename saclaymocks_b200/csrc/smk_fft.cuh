@@ -224,7 +224,7 @@ SMK_PLAN(512, 8, 8, 8)
 SMK_PLAN(768, 16, 16, 3)
 SMK_PLAN(1024, 16, 16, 4)
 SMK_PLAN(2048, 16, 16, 8)
-SMK_PLAN(2560, 8, 8, 8, 5)
+SMK_PLAN(2560, 16, 16, 2, 5)
 SMK_PLAN(4096, 16, 16, 16)
 #undef SMK_PLAN
 

@@ -30,7 +30,15 @@ struct PassAddr {
   long long hi_stride;
   long long lo_stride;
   int nsplit;
+  unsigned magic = 0, shift = 0;   // n / nsplit == umulhi(n, magic) >> shift for 0 <= n < 65536
 };
+
+// n / nsplit == umulhi(n, magic) for 0 <= n < 65536 and 2 <= nsplit <= 65536 (magic = floor(2^32 / d) + 1:
+// the error n * (magic * d - 2^32) stays below 2^32)
+inline void make_fastdiv(PassAddr& a) {
+  a.shift = 0;
+  a.magic = a.nsplit >= 2 ? (unsigned)((1ull << 32) / (unsigned)a.nsplit + 1) : 0u;
+}
 
 struct MulArgs {
   // spectral weight table W[n][outer][col] (float) with its own strides, or null
