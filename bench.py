@@ -49,30 +49,9 @@ def synthetic_qsos(nx, ny, seed=42):
 
 
 def weight_tables_device(bs, device):
-    """sqrt(P(|k|)/Vcell) for Pln1..3, P0 on this rank's k-slab, evaluated on the GPU from a fine 1-D table of the
-    oracle-independent spline.  Bench input preparation only (not timed, not the product path): parity runs use the
-    exact tables of interpolate_pk."""
-    import torch
-    from saclaymocks_b200 import pk
-    out = {}
-    k_ny = np.pi / bs.dcell
-    kx = torch.as_tensor(np.float32(np.fft.fftfreq(bs.NX) * 2 * k_ny), device=device)
-    ky = torch.as_tensor(np.float32(np.fft.fftfreq(bs.NY) * 2 * k_ny), device=device)
-    ky = ky[bs.rank * bs.nyl:(bs.rank + 1) * bs.nyl]
-    kz = torch.as_tensor(np.float32(np.fft.rfftfreq(bs.NZ) * 2 * k_ny), device=device)
-    kmax = float(np.sqrt(3.0) * k_ny * 1.001)
-    for name in ("Pln1", "Pln2", "Pln3", "P0"):
-        kk, ww = pk.weight_curve(name, bs.dcell, kmax, n=1 << 20)
-        tab = torch.as_tensor(np.float32(ww), device=device)
-        dk = float(kk[1] - kk[0])
-        W = torch.empty((bs.NX, bs.nyl, bs.nzh), dtype=torch.float32, device=device)
-        for i0 in range(0, bs.NX, 64):
-            k = torch.sqrt(kx[i0:i0 + 64, None, None] ** 2 + ky[None, :, None] ** 2 + kz[None, None, :] ** 2) / dk
-            j = k.floor().clamp_(0, len(ww) - 2).long()
-            f = k - j
-            W[i0:i0 + 64] = tab[j] * (1 - f) + tab[j + 1] * f
-        out[name] = W
-    return out
+    """The four spectral weight tables of this rank's k-slab, evaluated on the GPU from the P(k) splines
+    (smk_pk_weights = GPU interpolate_pk; input preparation, outside the timed region)."""
+    return {name: bs.weight_table(name) for name in ("Pln1", "Pln2", "Pln3", "P0")}
 
 
 # ------------------------------------------------------------------------------------------------ clocks

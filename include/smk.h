@@ -72,6 +72,13 @@ int smk_sync(smk_ctx* ctx);                       /* cudaStreamSynchronize(ctx s
 int smk_timing_enable(smk_ctx* ctx, int on);
 int smk_timing_collect(smk_ctx* ctx, double ms_sum[6], int count[6]);
 
+/* ---- spectral weight table of one product on the GPU (replaces the interpolate_pk.py / merge_pk.py stage,
+ * bin/interpolate_pk.py:17-26, 63-77): wtable[x][y_local][kz] = float32(sqrt(float32(max(S(|k|), 0)) / Vcell)) with S
+ * the cubic spline given in piecewise-polynomial form: breaks[nint+1] (ascending), coefs[4][nint] (highest power
+ * first, scipy.interpolate.PPoly convention), both device float64; the end intervals extrapolate like FITPACK.
+ * wtable: device float [nx][ny/R][nz/2+1], directly usable as the `wtable` argument of smk_synth_c2r. */
+int smk_pk_weights(smk_ctx* ctx, const double* breaks, const double* coefs, int nint, float* wtable);
+
 /* ---- white noise.  Replaces the np.random.normal plane loop of DrawGRF_boxk (make_boxes.py:46-48)
  * with Philox4x32-10 keyed by (seed, global cell index): identical for any slab decomposition. */
 int smk_noise_philox(smk_ctx* ctx, uint64_t seed, float* box_slab);

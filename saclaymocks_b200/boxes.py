@@ -78,6 +78,18 @@ class BoxSynth(object):
         assert tuple(t.shape) == (self.NX, self.nyl, self.nzh), t.shape
         return t
 
+    def weight_table(self, name):
+        """One HDU of P<NX>-<NY>-<NZ>.fits (this rank's ky rows) evaluated on the GPU from the P(k) spline
+        (interpolate_pk.py:17-26): name in Pln1, Pln2, Pln3, P0."""
+        from . import pk
+        br, co = pk.ppoly(name)
+        br_d = torch.as_tensor(br, device=self.device)
+        co_d = torch.as_tensor(co, device=self.device)
+        W = torch.empty((self.NX, self.nyl, self.nzh), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.smk_pk_weights(self.h, _ptr(br_d), _ptr(co_d), int(co.shape[1]), _ptr(W)))
+        torch.cuda.current_stream(self.device).synchronize()      # br_d / co_d may be released after this
+        return W
+
     # ------------------------------------------------------------------ DrawGRF_boxk (make_boxes.py:40-72)
     def noise_philox(self, seed):
         box = self.empty_box()

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmk.so")
-SOURCES = ["smk_boxes.cu", "smk_skewers.cu", "smk_spectra1d.cu", "smk_capi.cu"]
+SOURCES = ["smk_boxes.cu", "smk_skewers.cu", "smk_spectra1d.cu", "smk_pk.cu", "smk_capi.cu"]
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -206,23 +206,35 @@ class ChunkPipeline(object):
     # ------------------------------------------------------------------ end-to-end through host buffers (1 GPU)
     def make_host_buffers(self, W_dev):
         bs = self.bs
-        host = {"W": {k: v.cpu().pin_memory() for k, v in W_dev.items()},
+        from . import pk
+        pp = {}
+        for k in W_dev:                     # P(k) splines in piecewise-polynomial form: the real inputs of the chunk
+            br, co = pk.ppoly(k)
+            pp[k] = (torch.from_numpy(br).pin_memory(), torch.from_numpy(co).pin_memory(),
+                     torch.empty(br.shape, dtype=torch.float64, device=self.device),
+                     torch.empty(co.shape, dtype=torch.float64, device=self.device))
+        host = {"pp": pp,
                 "box": [torch.empty((bs.NX, bs.NY, bs.NZ), dtype=torch.float32).pin_memory() for _ in range(2)],
                 "spec": [torch.empty(self.out[0].shape, dtype=torch.float32).pin_memory() for _ in range(4)],
                 "copy_stream": torch.cuda.Stream(device=self.device)}
-        host["h2d_bytes"] = sum(v.numel() * 4 for v in host["W"].values()) + self.cat["xyzr"].nbytes + self.cat["nfor"].nbytes
+        host["h2d_bytes"] = (sum(v[0].numel() * 8 + v[1].numel() * 8 for v in pp.values()) + self.cat["xyzr"].nbytes
+                             + self.cat["nfor"].nbytes)
         host["d2h_bytes"] = len(PRODUCTS) * bs.NX * bs.NY * bs.NZ * 4 + 4 * self.out[0].numel() * 4
         return host
 
     def step_e2e(self, host, seed=0):
-        """Host weight tables in (pinned), every box and every spectrum row out to host memory.  The two pinned box
-        buffers stand for the FITS writer's staging area; copies overlap the next product's transforms."""
+        """Host inputs in (P(k) splines and the quasar catalogue, pinned), every box and every spectrum row out to
+        host memory.  The spectral weight tables are evaluated on the GPU (smk_pk_weights) inside the step.  The two
+        pinned box buffers stand for the FITS writer's staging area; copies overlap the next product's transforms."""
         assert self.nranks == 1
         main = torch.cuda.current_stream(self.device)
         cs = host["copy_stream"]
         self.stats.zero_()
-        for k in self.W:
-            self.W[k].copy_(host["W"][k], non_blocking=True)
+        for k, (br_h, co_h, br_d, co_d) in host["pp"].items():
+            br_d.copy_(br_h, non_blocking=True)
+            co_d.copy_(co_h, non_blocking=True)
+            _lib.check(self.bs.lib.smk_pk_weights(self.bs.h, _ptr(br_d), _ptr(co_d), int(co_h.shape[1]),
+                                                  _ptr(self.W[k])))
         c = self.cat
         c["xyzr_d"].copy_(torch.from_numpy(c["xyzr"]), non_blocking=True)
         c["nfor_d"].copy_(torch.from_numpy(c["nfor"]), non_blocking=True)

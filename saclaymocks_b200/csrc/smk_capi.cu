@@ -134,6 +134,13 @@ int smk_sync(smk_ctx* c) {
   return SMK_OK;
 }
 
+int smk_pk_weights(smk_ctx* c, const double* breaks, const double* coefs, int nint, float* wtable) {
+  if (!breaks || !coefs || nint < 1 || !wtable) { set_error("smk_pk_weights: bad argument"); return SMK_ERR_ARG; }
+  PkParams p{breaks, coefs, nint, c->kx, c->ky, c->kz, c->nx, c->nyl, c->nzh, c->rank * c->nyl,
+             (float)(c->dcell * c->dcell * c->dcell), wtable};
+  return launch_pk_weights(p, c->stream);
+}
+
 int smk_timing_enable(smk_ctx* c, int on) {
   c->timing = on != 0;
   c->ev_used = 0;

@@ -70,6 +70,17 @@ int launch_c2r_z(int NZ, const float2* in, float* out, long long nlines, int pit
 
 int launch_philox_fill(float* out, long long ncells, uint64_t seed, long long cell0, cudaStream_t st);
 
+struct PkParams {
+  const double* breaks;   // [nint+1]
+  const double* coefs;    // [4][nint], highest power first (scipy PPoly convention)
+  int nint;
+  const float *kx, *ky, *kz;
+  int nx, nyl, nzh, y0;
+  float vcell;
+  float* out;             // [nx][nyl][nzh]
+};
+int launch_pk_weights(const PkParams& p, cudaStream_t st);
+
 bool strided_size_supported(int n);
 bool z_size_supported(int nz);
 

@@ -86,3 +86,12 @@ def weight_curve(name, dcell, kmax, n=1 << 20):
     """sqrt(P(k)/Vcell) sampled on a uniform k grid (for fast table look-ups when exactness is not needed)."""
     k = np.linspace(0.0, kmax, n)
     return k, np.sqrt(np.maximum(spline(name)(k), 0) / dcell ** 3)
+
+
+def ppoly(name):
+    """Piecewise-polynomial form of spline(name): (breaks[n+1], coefs[4][n]) float64, for smk_pk_weights."""
+    from scipy.interpolate import PPoly
+    pp = PPoly.from_spline(spline(name)._eval_args)
+    x, c = pp.x, pp.c
+    keep = np.diff(x) > 0                       # drop the zero-length intervals of the repeated end knots
+    return np.ascontiguousarray(np.concatenate((x[:-1][keep], x[-1:]))), np.ascontiguousarray(c[:, keep])

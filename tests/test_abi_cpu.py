@@ -1,0 +1,44 @@
+"""The C-ABI library builds for sm_100a without a GPU, loads, and exports every symbol include/smk.h declares
+(no compute call is made here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+def declared_functions():
+    txt = open(os.path.join(ROOT, "include", "smk.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(smk_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_loads_and_exports_the_header():
+    from saclaymocks_b200 import build, _lib
+    lib = ctypes.CDLL(build.build())
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libsmk.so does not export %s declared in include/smk.h" % n
+    for n in _lib.EXPORTS:
+        assert n in names, "%s is bound by _lib.py but not declared in include/smk.h" % n
+    assert lib.smk_version() >= 100
+
+
+def test_python_binding_matches_header():
+    from saclaymocks_b200 import _lib
+    L = _lib.lib()
+    for n in declared_functions():
+        assert getattr(L, n) is not None
+    assert ctypes.sizeof(_lib.Geom) == 3 * 4 + 4 + 4 * 8 + 4 + 4 + 8     # smk_geom with C padding
+
+
+def test_product_refuses_to_run_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from saclaymocks_b200 import _lib
+    from saclaymocks_b200.boxes import BoxSynth
+    with pytest.raises(_lib.SmkError):
+        BoxSynth(16, 16, 24, 2.19)

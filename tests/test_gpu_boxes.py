@@ -119,3 +119,22 @@ def test_unsupported_shape_fails_loudly(cuda):
     from saclaymocks_b200.boxes import BoxSynth
     with pytest.raises(_lib.SmkError):
         BoxSynth(24, 24, 24, 2.19, device=cuda)
+
+
+@pytest.mark.parametrize("shape,dcell", [((16, 16, 96), 35.04), ((64, 32, 64), 2.19)])
+def test_gpu_weight_tables_match_interpolate_pk(cuda, shape, dcell, golden_small):
+    """smk_pk_weights (GPU interpolate_pk) against the host spline tables / the reference's P-file."""
+    from saclaymocks_b200 import pk
+    from saclaymocks_b200.boxes import BoxSynth
+    NX, NY, NZ = shape
+    bs = BoxSynth(NX, NY, NZ, dcell, device=cuda)
+    ref = pk.weight_tables(NX, NY, NZ, dcell)
+    for name in ("Pln1", "Pln2", "Pln3", "P0"):
+        got = bs.weight_table(name).cpu().numpy()
+        r = ref[name]
+        if shape == (16, 16, 96):
+            r = golden_small["W_" + name]                      # written by the unmodified interpolate_pk.py
+        same = (got == r).mean()
+        assert same > 0.999, (name, same)                      # float64 power basis vs FITPACK B-splines: rare 1-ulp ties
+        assert np.max(np.abs(got - r) / np.maximum(np.abs(r), 1e-30)) < 2.5e-7, name
+    bs.close()
