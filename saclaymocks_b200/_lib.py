@@ -14,7 +14,8 @@ PRODUCT_ID = {n: i for i, n in enumerate(PRODUCT_NAMES)}
 EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy", "smk_boxk_pitch", "smk_boxk_elems",
            "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
            "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
-           "smk_make_boxes_host", "smk_skewers", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights")
+           "smk_make_boxes_host", "smk_skewers", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
+           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p")
 
 
 class SmkError(RuntimeError):
@@ -63,10 +64,16 @@ def lib():
     L.smk_smallscale.argtypes = [vp, i, i, i, vp, u64, vp, vp, vp, vp, vp, vp]
     L.smk_fgpa.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.smk_pk_weights.argtypes = [vp, vp, vp, i, vp]
+    L.smk_exchange_create.argtypes = [vp, i]
+    L.smk_exchange_handle.argtypes = [vp, i, vp]
+    L.smk_exchange_connect.argtypes = [vp, i, vp]
+    L.smk_exchange_ptr.argtypes = [vp, i]
+    L.smk_exchange_ptr.restype = vp
+    L.smk_synth_c2r_local_p2p.argtypes = [vp, vp, i, vp, i, d, i]
     L.smk_timing_enable.argtypes = [vp, i]
     L.smk_timing_collect.argtypes = [vp, C.POINTER(d), C.POINTER(i)]
     for name in EXPORTS:
-        if name not in ("smk_last_error", "smk_boxk_elems", "smk_box_elems", "smk_workspace_bytes"):
+        if name not in ("smk_last_error", "smk_boxk_elems", "smk_box_elems", "smk_workspace_bytes", "smk_exchange_ptr"):
             getattr(L, name).restype = i
     _lib = L
     return L

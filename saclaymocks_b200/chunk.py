@@ -7,6 +7,7 @@ NVLink).  Skewer pixels are computed by the rank whose slab owns them (make_spec
 exchange of dmax planes per side.  No data-path collective exists in the skewer stage besides that halo.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -44,10 +45,34 @@ class ChunkPipeline(object):
             self.sendbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
             self.recvbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
             self.sendbuf, self.recvbuf = self.sendbufs[0], self.recvbufs[0]
+            self.p2p = os.environ.get("SMK_P2P", "1") != "0"
+            if self.p2p:
+                self._connect_exchange()
         self.W = None
         self.cat = None
         # kernels per step: 3 forward passes + 13 x 3 inverse passes + gather + small-scale + FGPA
         self.launches_per_step = 3 + 13 * 3 + 3
+
+    def _connect_exchange(self):
+        """Fused exchange set-up: two receive buffers per rank, mapped into every peer through CUDA IPC."""
+        import torch.distributed as dist
+        L, h = self.bs.lib, self.bs.h
+        _lib.check(L.smk_exchange_create(h, 2))
+        for b in range(2):
+            mine = (C.c_ubyte * 64)()
+            _lib.check(L.smk_exchange_handle(h, b, mine))
+            allh = [None] * self.nranks
+            dist.all_gather_object(allh, bytes(mine), group=self.group)
+            blob = (C.c_ubyte * (64 * self.nranks)).from_buffer_copy(b"".join(allh))
+            _lib.check(L.smk_exchange_connect(h, b, blob))
+        self._xptr = [L.smk_exchange_ptr(h, b) for b in range(2)]
+        self._tok = torch.zeros(1, dtype=torch.float32, device=self.device)
+        dist.barrier(group=self.group)
+
+    def _stream_barrier(self):
+        """Cross-rank barrier in stream order (a one-element all-reduce): when it completes on this rank's stream,
+        every rank's kernels enqueued before its own barrier have finished, so their peer stores are visible."""
+        torch.distributed.all_reduce(self._tok, group=self.group)
 
     # ------------------------------------------------------------------ inputs
     def set_weights(self, W):
@@ -128,6 +153,19 @@ class ChunkPipeline(object):
         # software pipeline over the independent inverse transforms (boxk is read-only after the 'box' product has
         # stored boxk*P0 back, and the products before it only read it): x pass of p | all-to-all of p-1 | y,z of p-2
         bs, L = self.bs, self.bs.lib
+        if self.p2p:
+            # fused exchange: the x pass of product i stores straight into every peer's receive buffer i&1; one
+            # stream-ordered barrier makes the stores visible and also protects the buffer written two products later
+            for i, name in enumerate(products):
+                slot = i & 1
+                pid = _lib.PRODUCT_ID[name]
+                wt = self.W[WEIGHT_OF[name]] if name in WEIGHT_OF else None
+                _lib.check(L.smk_synth_c2r_local_p2p(bs.h, _ptr(self.boxk), pid, _ptr(wt), 1, C.c_double(bs.dgrowth0),
+                                                     slot))
+                self._stream_barrier()
+                _lib.check(L.smk_synth_c2r_finish(bs.h, C.c_void_p(self._xptr[slot]), _ptr(self.interior(name)),
+                                                  _ptr(self.stats[pid])))
+            return
         pending = None            # (work, slot, name)
         for i, name in enumerate(products):
             slot = i & 1

@@ -46,6 +46,9 @@ struct StridedParams {
   int wcols;       // valid columns of the weight table rows (nz/2+1)
   MulArgs mul;
   const float2* tw;
+  // peer mode (fused exchange): output point k goes to rank k / aout.nsplit, into peer[rank] (that rank's receive
+  // buffer, already offset to this rank's chunk) at (k % nsplit) * lo_stride + outer * outer_stride + column
+  float2* peer[SMK_MAX_RANKS];
 };
 
 // element offset of point n: plain stride, or the two-level [hi][lo] form left behind by an all-to-all
@@ -57,7 +60,9 @@ __device__ __forceinline__ long long point_off(const PassAddr& a, int n) {
   return hi * a.hi_stride + lo * a.lo_stride;
 }
 
-template <int N, bool INV, int MUL, bool SPLIT_IN, bool SPLIT_OUT>
+enum { OUT_PLAIN = 0, OUT_SPLIT = 1, OUT_PEER = 2 };
+
+template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
 __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || StridedTraits<N>::MINB == 1)
                                                               ? StridedTraits<N>::MINB
                                                               : StridedTraits<N>::MINB - 1)
@@ -114,7 +119,16 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
     const double f = (double)f32 * p.mul.vscale;
     return make_float2((float)(-(double)v.y * f), (float)((double)v.x * f));
   };
-  auto st_g = [&](int, int k, float2 val) { outl[point_off<SPLIT_OUT>(p.aout, k)] = val; };
+  const long long peer_off = outer * p.aout.outer_stride + col;
+  auto st_g = [&](int, int k, float2 val) {
+    if (SPLIT_OUT == OUT_PEER) {
+      // fused all-to-all: the store goes over NVLink straight into the owner's receive buffer
+      const int hi = (int)__umulhi((unsigned)k, p.aout.magic), lo = k - hi * p.aout.nsplit;
+      p.peer[hi][peer_off + lo * p.aout.lo_stride] = val;
+    } else {
+      outl[point_off<SPLIT_OUT == OUT_SPLIT>(p.aout, k)] = val;
+    }
+  };
   auto st_s = [&](int line, int pos, float2 val) { sm[pos * LINES + line] = val; };
   auto ld_s = [&](int line, int pos, int, int) { return sm[pos * LINES + line]; };
 
@@ -128,7 +142,7 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
   }
 }
 
-template <int N, bool INV, int MUL, bool SPLIT_IN, bool SPLIT_OUT>
+template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
 static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st) {
   constexpr int LINES = StridedTraits<N>::LINES;
   constexpr int NT = StridedTraits<N>::NT;
@@ -143,21 +157,31 @@ static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st)
 }
 
 template <int N>
-static int launch_strided_n(bool inv, int mul, const StridedParams& p, int nouter, cudaStream_t st) {
+static int launch_strided_n(bool inv, int mul, const StridedParams& p, int nouter, bool peer, cudaStream_t st) {
   const bool si = p.ain.nsplit < N, so = p.aout.nsplit < N;
   if (!inv) {
-    if (mul != MUL_NONE || si) { set_error("forward pass: unsupported variant"); return SMK_ERR_ARG; }
-    return so ? launch_strided_t<N, false, MUL_NONE, false, true>(p, nouter, st)
-              : launch_strided_t<N, false, MUL_NONE, false, false>(p, nouter, st);
+    if (mul != MUL_NONE || si || peer) { set_error("forward pass: unsupported variant"); return SMK_ERR_ARG; }
+    return so ? launch_strided_t<N, false, MUL_NONE, false, OUT_SPLIT>(p, nouter, st)
+              : launch_strided_t<N, false, MUL_NONE, false, OUT_PLAIN>(p, nouter, st);
+  }
+  if (peer) {
+    if (si || !so) { set_error("peer pass: unsupported addressing"); return SMK_ERR_ARG; }
+    switch (mul) {
+      case MUL_TABLE: return launch_strided_t<N, true, MUL_TABLE, false, OUT_PEER>(p, nouter, st);
+      case MUL_ETA: return launch_strided_t<N, true, MUL_ETA, false, OUT_PEER>(p, nouter, st);
+      case MUL_VEL: return launch_strided_t<N, true, MUL_VEL, false, OUT_PEER>(p, nouter, st);
+    }
+    set_error("peer pass: bad multiplier mode");
+    return SMK_ERR_ARG;
   }
   if (so) { set_error("inverse pass: unsupported variant"); return SMK_ERR_ARG; }
   switch (mul) {
     case MUL_NONE:
-      return si ? launch_strided_t<N, true, MUL_NONE, true, false>(p, nouter, st)
-                : launch_strided_t<N, true, MUL_NONE, false, false>(p, nouter, st);
-    case MUL_TABLE: if (si) break; return launch_strided_t<N, true, MUL_TABLE, false, false>(p, nouter, st);
-    case MUL_ETA: if (si) break; return launch_strided_t<N, true, MUL_ETA, false, false>(p, nouter, st);
-    case MUL_VEL: if (si) break; return launch_strided_t<N, true, MUL_VEL, false, false>(p, nouter, st);
+      return si ? launch_strided_t<N, true, MUL_NONE, true, OUT_PLAIN>(p, nouter, st)
+                : launch_strided_t<N, true, MUL_NONE, false, OUT_PLAIN>(p, nouter, st);
+    case MUL_TABLE: if (si) break; return launch_strided_t<N, true, MUL_TABLE, false, OUT_PLAIN>(p, nouter, st);
+    case MUL_ETA: if (si) break; return launch_strided_t<N, true, MUL_ETA, false, OUT_PLAIN>(p, nouter, st);
+    case MUL_VEL: if (si) break; return launch_strided_t<N, true, MUL_VEL, false, OUT_PLAIN>(p, nouter, st);
   }
   set_error("bad multiplier mode / addressing combination");
   return SMK_ERR_ARG;
@@ -173,12 +197,17 @@ bool strided_size_supported(int n) {
 }
 
 int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, float2* out, PassAddr ain, PassAddr aout,
-                       int nouter, int ncols, int wcols, const MulArgs& mul, const float2* tw, cudaStream_t st) {
+                       int nouter, int ncols, int wcols, const MulArgs& mul, const float2* tw, cudaStream_t st,
+                       float2* const* peers, int npeers) {
   make_fastdiv(ain);
   make_fastdiv(aout);
-  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw};
+  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw, {nullptr}};
+  if (peers) {
+    if (npeers > SMK_MAX_RANKS) { set_error("too many ranks for the fused exchange"); return SMK_ERR_ARG; }
+    for (int i = 0; i < npeers; ++i) p.peer[i] = peers[i];
+  }
   switch (N) {
-#define X(N_) case N_: return launch_strided_n<N_>(inverse, mul_mode, p, nouter, st);
+#define X(N_) case N_: return launch_strided_n<N_>(inverse, mul_mode, p, nouter, peers != nullptr, st);
     SMK_STRIDED_SIZES(X)
 #undef X
   }

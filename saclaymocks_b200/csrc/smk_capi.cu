@@ -23,6 +23,11 @@ struct smk_ctx {
   float2* work = nullptr;      // [nxl][ny][pitch] (== boxk size)
   double* stats = nullptr;     // scratch for the host wrapper
   size_t bytes = 0;
+  // fused exchange (smk_exchange_*): receive buffers of this rank and the peers' views of theirs
+  int nxbuf = 0;
+  float2* xbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+  float2* xpeer[4][SMK_MAX_RANKS] = {};
+  bool xconnected[4] = {false, false, false, false};
   // optional per-pass CUDA-event timing (smk_timing_*): events are recorded around every pass kernel
   bool timing = false;
   std::vector<cudaEvent_t> ev;       // pool
@@ -120,6 +125,11 @@ int smk_ctx_destroy(smk_ctx* c) {
   cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->tw_z);
   cudaFree(c->kx); cudaFree(c->ky); cudaFree(c->kz);
   cudaFree(c->work); cudaFree(c->stats);
+  for (int b = 0; b < c->nxbuf; ++b) {
+    for (int r = 0; r < c->nranks; ++r)
+      if (c->xconnected[b] && r != c->rank && c->xpeer[b][r]) cudaIpcCloseMemHandle(c->xpeer[b][r]);
+    cudaFree(c->xbuf[b]);
+  }
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   delete c;
   return SMK_OK;
@@ -231,6 +241,82 @@ int smk_synth_c2r_local(smk_ctx* c, void* boxk, int product, const float* wtable
   tmark(c, PASS_INV_X);
   int rc = launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, (float2*)sendbuf, a, a, c->nyl, c->pitch, c->nzh, m,
                               c->tw_x, c->stream);
+  tmark(c, -1);
+  return rc;
+}
+
+// ---- fused exchange: the inverse x pass stores straight into the peers' receive buffers over NVLink
+int smk_exchange_create(smk_ctx* c, int nbuf) {
+  if (nbuf < 1 || nbuf > 4 || c->nxbuf) { set_error("smk_exchange_create: nbuf must be 1..4, once per ctx"); return SMK_ERR_ARG; }
+  size_t bytes = smk_boxk_elems(c) * sizeof(float2);
+  for (int b = 0; b < nbuf; ++b) {
+    SMK_CUDA_OK(cudaMalloc(&c->xbuf[b], bytes));
+    SMK_CUDA_OK(cudaMemset(c->xbuf[b], 0, bytes));
+    c->bytes += bytes;
+  }
+  c->nxbuf = nbuf;
+  return SMK_OK;
+}
+
+int smk_exchange_handle(smk_ctx* c, int buf, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (buf < 0 || buf >= c->nxbuf) { set_error("smk_exchange_handle: bad buffer index"); return SMK_ERR_ARG; }
+  cudaIpcMemHandle_t h;
+  SMK_CUDA_OK(cudaIpcGetMemHandle(&h, c->xbuf[buf]));
+  memcpy(handle, &h, 64);
+  return SMK_OK;
+}
+
+int smk_exchange_connect(smk_ctx* c, int buf, const unsigned char* handles) {
+  if (buf < 0 || buf >= c->nxbuf || !handles) { set_error("smk_exchange_connect: bad argument"); return SMK_ERR_ARG; }
+  if (c->nranks > SMK_MAX_RANKS) { set_error("smk_exchange_connect: too many ranks"); return SMK_ERR_ARG; }
+  for (int r = 0; r < c->nranks; ++r) {
+    if (r == c->rank) { c->xpeer[buf][r] = c->xbuf[buf]; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * r, 64);
+    void* ptr = nullptr;
+    SMK_CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->xpeer[buf][r] = (float2*)ptr;
+  }
+  c->xconnected[buf] = true;
+  return SMK_OK;
+}
+
+void* smk_exchange_ptr(smk_ctx* c, int buf) { return (buf >= 0 && buf < c->nxbuf) ? c->xbuf[buf] : nullptr; }
+
+int smk_synth_c2r_local_p2p(smk_ctx* c, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
+                            int buf) {
+  if (buf < 0 || buf >= c->nxbuf || !c->xconnected[buf]) { set_error("smk_synth_c2r_local_p2p: exchange buffer not connected"); return SMK_ERR_ARG; }
+  if (c->nranks < 2 || c->nxl < 2) { set_error("smk_synth_c2r_local_p2p: needs >= 2 ranks and >= 2 planes per rank"); return SMK_ERR_ARG; }
+  if (product < 0 || product >= SMK_NPRODUCTS) { set_error("bad product id"); return SMK_ERR_ARG; }
+  MulArgs m{};
+  int mode;
+  if (product <= SMK_P0) {
+    if (!wtable) { set_error("spectral weight table required for products PLN1..P0"); return SMK_ERR_ARG; }
+    mode = MUL_TABLE;
+    m.wt = wtable;
+    m.wt_n_stride = (long long)c->nyl * c->nzh;
+    m.wt_outer_stride = c->nzh;
+    m.store_back = (product == SMK_P0 && store_p0) ? (float2*)boxk : nullptr;
+  } else {
+    static const int FA[] = {0, 1, 2, 0, 0, 1, 0, 1, 2};
+    static const int FB[] = {0, 1, 2, 1, 2, 2, 0, 0, 0};
+    mode = product >= SMK_VX ? MUL_VEL : MUL_ETA;
+    m.kn = c->kx; m.ko = c->ky; m.kc = c->kz;
+    m.outer0 = c->rank * c->nyl;
+    m.fa = FA[product - SMK_ETA_XX];
+    m.fb = FB[product - SMK_ETA_XX];
+    m.vscale = dgrowth0;
+  }
+  // receive layout on rank d: [src][x_l][y_l][kz]; this rank is `src`
+  const long long chunk = (long long)c->nxl * c->nyl * c->pitch;
+  float2* peers[SMK_MAX_RANKS];
+  for (int r = 0; r < c->nranks; ++r) peers[r] = c->xpeer[buf][r] + (long long)c->rank * chunk;
+  PassAddr ain{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
+  PassAddr aout{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nxl};   // hi = x / nxl selects the peer
+  tmark(c, PASS_INV_X);
+  int rc = launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, nullptr, ain, aout, c->nyl, c->pitch, c->nzh, m,
+                              c->tw_x, c->stream, peers, c->nranks);
   tmark(c, -1);
   return rc;
 }

@@ -7,6 +7,8 @@
 
 #include "../../include/smk.h"
 
+#define SMK_MAX_RANKS 16
+
 namespace smk {
 
 void set_error(const std::string& msg);
@@ -60,7 +62,8 @@ struct MulArgs {
 enum MulMode { MUL_NONE = 0, MUL_TABLE = 1, MUL_ETA = 2, MUL_VEL = 3 };
 
 int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, float2* out, PassAddr ain, PassAddr aout,
-                       int nouter, int ncols, int wcols, const MulArgs& mul, const float2* tw, cudaStream_t st);
+                       int nouter, int ncols, int wcols, const MulArgs& mul, const float2* tw, cudaStream_t st,
+                       float2* const* peers = nullptr, int npeers = 0);
 
 int launch_r2c_z(int NZ, const float* in, float2* out, long long nlines, int pitch, const float2* tw,
                  bool philox, uint64_t seed, long long cell0, cudaStream_t st);
