@@ -64,6 +64,7 @@ size_t smk_boxk_elems(const smk_ctx* ctx);        /* complex elements of this ra
 size_t smk_box_elems(const smk_ctx* ctx);         /* float elements of this rank's real x-slab */
 size_t smk_workspace_bytes(const smk_ctx* ctx);   /* bytes the ctx holds in HBM */
 int smk_sync(smk_ctx* ctx);                       /* cudaStreamSynchronize(ctx stream) */
+int smk_set_stream(smk_ctx* ctx, void* stream);   /* later calls launch on this cudaStream_t (host-side switch only) */
 
 /* ---- per-pass device timing for the roofline report (bench.py).  When enabled, CUDA events are recorded on the
  * ctx stream around every FFT pass kernel; smk_timing_collect synchronises the stream and returns, per pass

@@ -15,7 +15,7 @@ EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy",
            "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
            "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
            "smk_make_boxes_host", "smk_skewers", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
-           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p")
+           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_set_stream")
 
 
 class SmkError(RuntimeError):
@@ -52,6 +52,7 @@ def lib():
     L.smk_workspace_bytes.argtypes = [vp]
     L.smk_workspace_bytes.restype = sz
     L.smk_sync.argtypes = [vp]
+    L.smk_set_stream.argtypes = [vp, vp]
     L.smk_noise_philox.argtypes = [vp, u64, vp]
     L.smk_fft_r2c.argtypes = [vp, vp, u64, vp]
     L.smk_fft_r2c_local.argtypes = [vp, vp, u64, vp]

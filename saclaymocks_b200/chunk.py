@@ -45,7 +45,11 @@ class ChunkPipeline(object):
             self.sendbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
             self.recvbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
             self.sendbuf, self.recvbuf = self.sendbufs[0], self.recvbufs[0]
-            self.p2p = os.environ.get("SMK_P2P", "1") != "0"
+            # fused peer-store exchange pays off when a tile row is a full 128-B line (x lengths up to 1024, 16 kz
+            # columns per tile); with the 8-column tiles of longer lines the 64-B NVLink writes reach only ~340 GB/s
+            # (measured, profiles/README.md), so those sizes keep the pipelined NCCL all-to-all.  SMK_P2P=0/1 forces.
+            mode = os.environ.get("SMK_P2P", "auto")
+            self.p2p = (NX <= 1024) if mode == "auto" else (mode != "0")
             if self.p2p:
                 self._connect_exchange()
         self.W = None
@@ -67,6 +71,7 @@ class ChunkPipeline(object):
             _lib.check(L.smk_exchange_connect(h, b, blob))
         self._xptr = [L.smk_exchange_ptr(h, b) for b in range(2)]
         self._tok = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._xstream = torch.cuda.Stream(device=self.device)
         dist.barrier(group=self.group)
 
     def _stream_barrier(self):
@@ -154,17 +159,35 @@ class ChunkPipeline(object):
         # stored boxk*P0 back, and the products before it only read it): x pass of p | all-to-all of p-1 | y,z of p-2
         bs, L = self.bs, self.bs.lib
         if self.p2p:
-            # fused exchange: the x pass of product i stores straight into every peer's receive buffer i&1; one
-            # stream-ordered barrier makes the stores visible and also protects the buffer written two products later
-            for i, name in enumerate(products):
-                slot = i & 1
+            # fused exchange, two streams: X runs the x pass of product q (NVLink-bound peer stores) while M runs the
+            # y and z passes of product q-1 (HBM-bound).  Per product, on X:  x(q) -> wait yz(q-2) -> barrier(q);
+            # on M: wait barrier(q) -> y,z(q).  barrier(q) completes only when every rank has finished x(q) (its stores
+            # into our buffer q&1 are visible) and yz(q-2) (buffer q&1 may be overwritten by x(q+2)... see below).
+            main = torch.cuda.current_stream(self.device)
+            X = self._xstream
+            X.wait_stream(main)                         # boxk (forward transform) is ready
+            ev_yz = [None, None]
+            for q, name in enumerate(products):
+                slot = q & 1
                 pid = _lib.PRODUCT_ID[name]
                 wt = self.W[WEIGHT_OF[name]] if name in WEIGHT_OF else None
-                _lib.check(L.smk_synth_c2r_local_p2p(bs.h, _ptr(self.boxk), pid, _ptr(wt), 1, C.c_double(bs.dgrowth0),
-                                                     slot))
-                self._stream_barrier()
+                with torch.cuda.stream(X):
+                    L.smk_set_stream(bs.h, C.c_void_p(X.cuda_stream))
+                    # x(q) overwrites buffer `slot` on the peers: they finished reading it (yz(q-2)) before they
+                    # entered barrier(q-1), which precedes x(q) on this stream
+                    _lib.check(L.smk_synth_c2r_local_p2p(bs.h, _ptr(self.boxk), pid, _ptr(wt), 1,
+                                                         C.c_double(bs.dgrowth0), slot))
+                    if ev_yz[slot ^ 1] is not None:
+                        X.wait_event(ev_yz[slot ^ 1])   # yz(q-1) done before this rank enters barrier(q)
+                    self._stream_barrier()
+                    ev_bar = torch.cuda.Event()
+                    ev_bar.record(X)
+                L.smk_set_stream(bs.h, C.c_void_p(main.cuda_stream))
+                main.wait_event(ev_bar)
                 _lib.check(L.smk_synth_c2r_finish(bs.h, C.c_void_p(self._xptr[slot]), _ptr(self.interior(name)),
                                                   _ptr(self.stats[pid])))
+                ev_yz[slot] = torch.cuda.Event()
+                ev_yz[slot].record(main)
             return
         pending = None            # (work, slot, name)
         for i, name in enumerate(products):

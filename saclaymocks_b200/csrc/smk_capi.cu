@@ -139,6 +139,11 @@ int smk_boxk_pitch(const smk_ctx* c) { return c->pitch; }
 size_t smk_boxk_elems(const smk_ctx* c) { return (size_t)c->nx * c->nyl * c->pitch; }
 size_t smk_box_elems(const smk_ctx* c) { return (size_t)c->nxl * c->ny * c->nz; }
 size_t smk_workspace_bytes(const smk_ctx* c) { return c->bytes; }
+int smk_set_stream(smk_ctx* c, void* stream) {
+  c->stream = (cudaStream_t)stream;
+  return SMK_OK;
+}
+
 int smk_sync(smk_ctx* c) {
   SMK_CUDA_OK(cudaStreamSynchronize(c->stream));
   return SMK_OK;
