@@ -114,15 +114,18 @@ int smk_synth_c2r_finish(smk_ctx* ctx, void* recvbuf, float* out_slab, double* s
  * smk_exchange_create allocates `nbuf` receive buffers (boxk-sized) inside the ctx; each rank publishes
  * smk_exchange_handle(buf) (a 64-byte cudaIpcMemHandle_t), gathers all ranks' handles (any host-side all-gather) and
  * calls smk_exchange_connect(buf, handles[nranks][64]).  smk_synth_c2r_local_p2p then replaces
- * smk_synth_c2r_local + all-to-all; the caller must order (a) a cross-rank barrier on the streams between the p2p x
- * pass and smk_synth_c2r_finish(ctx, smk_exchange_ptr(buf), ...), and (b) reuse of a buffer only after every rank has
- * finished reading it (two buffers used alternately with one barrier per product satisfy both). */
+ * smk_synth_c2r_local + all-to-all and smk_synth_c2r_finish_p2p replaces smk_synth_c2r_finish (the receive buffers use
+ * a tiled layout [src][kz tile][y_l][x_l][tile width], in which each x-pass tile owns one contiguous run per
+ * destination, so the peer stores are 512-B contiguous per warp).  The caller must order (a) a cross-rank barrier on
+ * the streams between the two calls and (b) reuse of a buffer only after every rank has finished reading it (two
+ * buffers used alternately with one barrier per product satisfy both). */
 int smk_exchange_create(smk_ctx* ctx, int nbuf);
 int smk_exchange_handle(smk_ctx* ctx, int buf, unsigned char handle[64]);
 int smk_exchange_connect(smk_ctx* ctx, int buf, const unsigned char* handles);
 void* smk_exchange_ptr(smk_ctx* ctx, int buf);
 int smk_synth_c2r_local_p2p(smk_ctx* ctx, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
                             int buf);
+int smk_synth_c2r_finish_p2p(smk_ctx* ctx, int buf, float* out_slab, double* stats);
 
 /* Host-buffer convenience wrapper of the whole DrawGRF_boxk + 13 x FFTandStore chain (the call a
  * make_boxes.py replacement makes): noise from `noise_host` ([nx][ny][nz] float) or Philox(seed) when NULL,

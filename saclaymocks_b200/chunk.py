@@ -45,11 +45,9 @@ class ChunkPipeline(object):
             self.sendbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
             self.recvbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
             self.sendbuf, self.recvbuf = self.sendbufs[0], self.recvbufs[0]
-            # fused peer-store exchange pays off when a tile row is a full 128-B line (x lengths up to 1024, 16 kz
-            # columns per tile); with the 8-column tiles of longer lines the 64-B NVLink writes reach only ~340 GB/s
-            # (measured, profiles/README.md), so those sizes keep the pipelined NCCL all-to-all.  SMK_P2P=0/1 forces.
-            mode = os.environ.get("SMK_P2P", "auto")
-            self.p2p = (NX <= 1024) if mode == "auto" else (mode != "0")
+            # fused peer-store exchange (default) or the pipelined NCCL all-to-all (SMK_P2P=0); measurements of both in
+            # profiles/README.md
+            self.p2p = os.environ.get("SMK_P2P", "1") != "0"
             if self.p2p:
                 self._connect_exchange()
         self.W = None
@@ -184,8 +182,7 @@ class ChunkPipeline(object):
                     ev_bar.record(X)
                 L.smk_set_stream(bs.h, C.c_void_p(main.cuda_stream))
                 main.wait_event(ev_bar)
-                _lib.check(L.smk_synth_c2r_finish(bs.h, C.c_void_p(self._xptr[slot]), _ptr(self.interior(name)),
-                                                  _ptr(self.stats[pid])))
+                _lib.check(L.smk_synth_c2r_finish_p2p(bs.h, slot, _ptr(self.interior(name)), _ptr(self.stats[pid])))
                 ev_yz[slot] = torch.cuda.Event()
                 ev_yz[slot].record(main)
             return

@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
   extern __shared__ float2 sm[];   // [N][LINES]
   const int col = blockIdx.x * LINES + threadIdx.x % LINES;   // this thread's kz column (fixed for the kernel)
   const int outer = blockIdx.y;
-  const float2* __restrict__ inl = p.in + (outer * p.ain.outer_stride + col);
+  const long long in_col = p.ain.tile_width ? (long long)(col / p.ain.tile_width) * p.ain.tile_stride + col % p.ain.tile_width
+                                            : (long long)col;
+  const float2* __restrict__ inl = p.in + (outer * p.ain.outer_stride + in_col);
   float2* __restrict__ outl = p.out + (outer * p.aout.outer_stride + col);
 
   // ---- fused multiply of make_boxes.py:247-429 (reference float32 rounding order), applied to the loaded element
@@ -119,20 +121,32 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
     const double f = (double)f32 * p.mul.vscale;
     return make_float2((float)(-(double)v.y * f), (float)((double)v.x * f));
   };
-  const long long peer_off = outer * p.aout.outer_stride + col;
-  auto st_g = [&](int, int k, float2 val) {
-    if (SPLIT_OUT == OUT_PEER) {
-      // fused all-to-all: the store goes over NVLink straight into the owner's receive buffer
-      const int hi = (int)__umulhi((unsigned)k, p.aout.magic), lo = k - hi * p.aout.nsplit;
-      p.peer[hi][peer_off + lo * p.aout.lo_stride] = val;
-    } else {
-      outl[point_off<SPLIT_OUT == OUT_SPLIT>(p.aout, k)] = val;
-    }
-  };
+  auto st_g = [&](int, int k, float2 val) { outl[point_off<SPLIT_OUT == OUT_SPLIT>(p.aout, k)] = val; };
   auto st_s = [&](int line, int pos, float2 val) { sm[pos * LINES + line] = val; };
   auto ld_s = [&](int line, int pos, int, int) { return sm[pos * LINES + line]; };
 
-  if constexpr (P::S == 1) {
+  if constexpr (SPLIT_OUT == OUT_PEER) {
+    // ---- fused exchange: finish the transform in shared memory in natural order, then copy every destination
+    //      rank's block (aout.nsplit = nx/R consecutive x rows of this tile = one contiguous run of the tiled receive
+    //      layout [src][kz tile][y_l][x_l][LINES]) over NVLink with 16-byte stores, 512 B per warp instruction
+    if constexpr (P::S == 1) {
+      dif_stage<P, 0, INV, LINES, NT, OUT_RESORT>(ld_g, st_s, p.tw, 1, pre);
+    } else {
+      dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE>(ld_g, st_s, p.tw, 1, pre);
+      __syncthreads();
+      dif_stages_smem<P, 1, P::S - 1, INV, LINES, 1, LINES, NT>(sm, p.tw, 1);
+      dif_stage<P, P::S - 1, INV, LINES, NT, OUT_RESORT>(ld_s, st_s, p.tw, 1);
+    }
+    __syncthreads();
+    const int per_dest = p.aout.nsplit * (LINES / 2);                       // float4 per destination block
+    const long long doff = blockIdx.x * p.aout.tile_stride + outer * p.aout.outer_stride;
+    const float4* sm4 = reinterpret_cast<const float4*>(sm);
+    for (int d = 0; d < N / p.aout.nsplit; ++d) {
+      float4* dst = reinterpret_cast<float4*>(p.peer[d] + doff);
+      const float4* src = sm4 + d * per_dest;
+      for (int e = threadIdx.x; e < per_dest; e += NT) dst[e] = src[e];
+    }
+  } else if constexpr (P::S == 1) {
     dif_stage<P, 0, INV, LINES, NT, OUT_NATURAL>(ld_g, st_g, p.tw, 1, pre);
   } else {
     dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE>(ld_g, st_s, p.tw, 1, pre);
@@ -188,6 +202,13 @@ static int launch_strided_n(bool inv, int mul, const StridedParams& p, int noute
 }
 
 #define SMK_STRIDED_SIZES(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(2560)
+
+int strided_tile_width(int n) {
+#define X(N_) if (n == N_) return StridedTraits<N_>::LINES;
+  SMK_STRIDED_SIZES(X)
+#undef X
+  return 0;
+}
 
 bool strided_size_supported(int n) {
 #define X(N_) if (n == N_) return true;

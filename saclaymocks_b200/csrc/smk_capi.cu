@@ -313,15 +313,40 @@ int smk_synth_c2r_local_p2p(smk_ctx* c, void* boxk, int product, const float* wt
     m.fb = FB[product - SMK_ETA_XX];
     m.vscale = dgrowth0;
   }
-  // receive layout on rank d: [src][x_l][y_l][kz]; this rank is `src`
+  // tiled receive layout on rank d: [src][kz tile][y_l][x_l][LX] (LX = kz columns per x-pass tile); this rank is `src`.
+  // One x-pass tile (one y_l, one kz tile) owns, per destination, a contiguous run of nxl*LX elements.
   const long long chunk = (long long)c->nxl * c->nyl * c->pitch;
+  const int LX = strided_tile_width(c->nx);
   float2* peers[SMK_MAX_RANKS];
   for (int r = 0; r < c->nranks; ++r) peers[r] = c->xpeer[buf][r] + (long long)c->rank * chunk;
   PassAddr ain{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
-  PassAddr aout{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nxl};   // hi = x / nxl selects the peer
+  PassAddr aout{(long long)c->nxl * LX, 0, 0, c->nxl};                        // nsplit = rows per destination
+  aout.tile_width = LX;
+  aout.tile_stride = (long long)c->nyl * c->nxl * LX;
   tmark(c, PASS_INV_X);
   int rc = launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, nullptr, ain, aout, c->nyl, c->pitch, c->nzh, m,
                               c->tw_x, c->stream, peers, c->nranks);
+  tmark(c, -1);
+  return rc;
+}
+
+int smk_synth_c2r_finish_p2p(smk_ctx* c, int buf, float* out_slab, double* stats) {
+  if (buf < 0 || buf >= c->nxbuf) { set_error("smk_synth_c2r_finish_p2p: bad buffer index"); return SMK_ERR_ARG; }
+  // y pass reading the tiled receive layout [src][kz tile][y_l][x_l][LX]: y = src*nyl + y_l
+  const long long chunk = (long long)c->nxl * c->nyl * c->pitch;
+  const int LX = strided_tile_width(c->nx);
+  PassAddr ain{(long long)LX, chunk, (long long)c->nxl * LX, c->nyl};
+  ain.tile_width = LX;
+  ain.tile_stride = (long long)c->nyl * c->nxl * LX;
+  PassAddr aout{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
+  MulArgs m{};
+  tmark(c, PASS_INV_Y);
+  int rc = launch_c2c_strided(c->ny, true, MUL_NONE, c->xbuf[buf], c->work, ain, aout, c->nxl, c->pitch, c->nzh, m,
+                              c->tw_y, c->stream);
+  if (rc) return rc;
+  float norm = (float)((double)c->nx * c->ny * c->nz);
+  tmark(c, PASS_C2R_Z);
+  rc = launch_c2r_z(c->nz, c->work, out_slab, (long long)c->nxl * c->ny, c->pitch, c->tw_z, norm, stats, c->stream);
   tmark(c, -1);
   return rc;
 }

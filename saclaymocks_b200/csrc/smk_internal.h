@@ -33,6 +33,10 @@ struct PassAddr {
   long long lo_stride;
   int nsplit;
   unsigned magic = 0, shift = 0;   // n / nsplit == umulhi(n, magic) >> shift for 0 <= n < 65536
+  // column addressing: plain rows (tile_width == 0: offset = column) or the tiled exchange layout, where groups of
+  // tile_width kz columns are stored tile_stride elements apart: offset = (col / tile_width) * tile_stride + col % tile_width
+  int tile_width = 0;
+  long long tile_stride = 0;
 };
 
 // n / nsplit == umulhi(n, magic) for 0 <= n < 65536 and 2 <= nsplit <= 65536 (magic = floor(2^32 / d) + 1:
@@ -85,6 +89,7 @@ struct PkParams {
 int launch_pk_weights(const PkParams& p, cudaStream_t st);
 
 bool strided_size_supported(int n);
+int strided_tile_width(int n);   // kz columns per tile of the strided pass of length n
 bool z_size_supported(int nz);
 
 }  // namespace smk

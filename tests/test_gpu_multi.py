@@ -12,12 +12,13 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, port, shape, dcell, out):
+def _worker(rank, world, port, shape, dcell, out, p2p):
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, HERE)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["SMK_P2P"] = p2p
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -77,14 +78,16 @@ def _worker(rank, world, port, shape, dcell, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shape", [(2, (32, 32, 96)), (2, (64, 32, 96)), (4, (64, 64, 96))])
-def test_sharded_pipeline_matches_oracle(tmp_path, world, shape):
+@pytest.mark.parametrize("world,shape,p2p", [(2, (32, 32, 96), "auto"), (2, (64, 32, 96), "0"), (2, (2048, 32, 96), "1"),
+                                             (4, (64, 64, 96), "auto")])
+def test_sharded_pipeline_matches_oracle(tmp_path, world, shape, p2p):
+    """p2p: "1" = fused peer-store exchange (tiled receive layout), "0" = NCCL all-to-all, "auto" = by size."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     out = str(tmp_path / "res")
     port = 29600 + world + shape[0]
-    mp.spawn(_worker, args=(world, port, shape, 3364.0 / shape[2], out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, shape, 3364.0 / shape[2], out, p2p), nprocs=world, join=True)
     pieces = 0
     for r in range(world):
         import json
