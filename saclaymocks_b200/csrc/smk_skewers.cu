@@ -141,12 +141,12 @@ __global__ void __launch_bounds__(128) skewers_kernel(SkewerParams p, int nchunk
 // its own window, which keeps the result identical to the reference's truncated Gaussian sum.
 template <int DMAX, int P, int NF, bool INTERIOR>
 __device__ __forceinline__ void gather_multi(const SkewerParams& p, const float* const (&fp)[NF], int bx, int by,
-                                             int bz, int nxu, int nyu, const int (&dix)[P], const int (&diy)[P],
-                                             const float (&ox)[P], const float (&oy)[P],
+                                             int bz, int nxu, int nyu, const int (&dix)[P], const float (&ox)[P],
+                                             const float* wy_s /* [b][q] of this thread, stride 128 */,
                                              const float (&wz)[P][2 * DMAX + 2], float inv_sig2, float (&acc)[NF][P],
-                                             float (&sx)[P], float (&sy)[P]) {
+                                             float (&sx)[P]) {
   constexpr int WU = 2 * DMAX + 2;
-  const float fdx = (float)p.dx, fdy = (float)p.dy;
+  const float fdx = (float)p.dx;
 #pragma unroll
   for (int f = 0; f < NF; ++f)
 #pragma unroll
@@ -156,7 +156,7 @@ __device__ __forceinline__ void gather_multi(const SkewerParams& p, const float*
   for (int c = 0; c < WU; ++c) lz[c] = INTERIOR ? c : min(max(bz - DMAX + c, 0), p.nz - 1);
   const int z0 = INTERIOR ? bz - DMAX : 0;      // INTERIOR: the z window [bz-DMAX, bz+DMAX+1] needs no clamping
 #pragma unroll
-  for (int q = 0; q < P; ++q) { sx[q] = 0.f; sy[q] = 0.f; }
+  for (int q = 0; q < P; ++q) sx[q] = 0.f;
   const unsigned plane = (unsigned)p.ny * (unsigned)p.nz;
   for (int a = 0; a < nxu; ++a) {
     const int la = INTERIOR ? (bx - DMAX + a - p.ix0) : min(max(bx - DMAX + a - p.ix0, 0), p.nxs - 1);
@@ -172,13 +172,7 @@ __device__ __forceinline__ void gather_multi(const SkewerParams& p, const float*
       const int lb = INTERIOR ? (by - DMAX + b) : min(max(by - DMAX + b, 0), p.ny - 1);
       float wab[P];
 #pragma unroll
-      for (int q = 0; q < P; ++q) {
-        const int m = b - DMAX - diy[q];
-        const float t = m * fdy + oy[q];
-        const float wyb = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
-        if (a == 0) sy[q] += wyb;
-        wab[q] = wxa[q] * wyb;
-      }
+      for (int q = 0; q < P; ++q) wab[q] = wxa[q] * wy_s[(b * P + q) * 128];
       const size_t row = (size_t)la * plane + (unsigned)lb * (unsigned)p.nz + z0;
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
@@ -265,22 +259,41 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
       sz[k] += wz[k][c];
     }
   }
+  // y weights of the union window, once per thread, shared by the two field-group passes: [b][q][thread]
+  __shared__ float s_wy[(2 * DMAX + 2) * P * 128];
+  float* wy_s = s_wy + threadIdx.x;
+  float sy[P];
+  {
+    const float fdy = (float)p.dy;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      sy[k] = 0.f;
+#pragma unroll
+      for (int b = 0; b < WU; ++b) {
+        const int m = b - DMAX - diy[k];
+        const float t = m * fdy + oy[k];
+        const float w = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
+        wy_s[(b * P + k) * 128] = w;
+        sy[k] += w;
+      }
+    }
+  }
   // whole union window inside the slab: no index clamping, z offsets become immediates
   const bool interior = bx - DMAX - p.ix0 >= 0 && bx - DMAX - p.ix0 + nxu <= p.nxs && by - DMAX >= 0 &&
                         by - DMAX + nyu <= p.ny && bz - DMAX >= 0 && bz + DMAX + 1 < p.nz;
-  float sx[P], sy[P];
+  float sx[P];
   const int NFI = p.rsd ? (p.dla ? 10 : 7) : 1;
   float d0[P], inv_sw[P];
   double eta[P], vel[P];
 #pragma unroll
   for (int k = 0; k < P; ++k) { eta[k] = 0.0; vel[k] = 0.0; }
-#define SMK_GATHER(NF_, ACC, SX, SY)                                                                              \
-  if (interior) gather_multi<DMAX, P, NF_, true>(p, fp, bx, by, bz, nxu, nyu, dix, diy, ox, oy, wz, inv_sig2, ACC, SX, SY); \
-  else gather_multi<DMAX, P, NF_, false>(p, fp, bx, by, bz, nxu, nyu, dix, diy, ox, oy, wz, inv_sig2, ACC, SX, SY);
+#define SMK_GATHER(NF_, ACC, SX, SY_UNUSED)                                                                              \
+  if (interior) gather_multi<DMAX, P, NF_, true>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz, inv_sig2, ACC, SX);    \
+  else gather_multi<DMAX, P, NF_, false>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz, inv_sig2, ACC, SX);
   if (NFI == 1) {
     float acc[1][P];
     const float* const fp[1] = {p.f[0]};
-    SMK_GATHER(1, acc, sx, sy)
+    SMK_GATHER(1, acc, sx, 0)
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       inv_sw[k] = ((actmask >> k) & 1) ? 1.0f / (sx[k] * sy[k] * sz[k]) : 0.f;
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
     {   // group A: delta, eta_xx, eta_yy, eta_zz, eta_xy
       float acc[5][P];
       const float* const fp[5] = {p.f[0], p.f[1], p.f[2], p.f[3], p.f[4]};
-      SMK_GATHER(5, acc, sx, sy)
+      SMK_GATHER(5, acc, sx, 0)
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         inv_sw[k] = ((actmask >> k) & 1) ? 1.0f / (sx[k] * sy[k] * sz[k]) : 0.f;
@@ -301,11 +314,11 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
                  zv * (double)(acc[3][k] * inv_sw[k]) * zv + 2 * xv * (double)(acc[4][k] * inv_sw[k]) * yv;
       }
     }
-    float sx2[P], sy2[P];
+    float sx2[P];
     if (NFI == 10) {   // group B: eta_xz, eta_yz, vx, vy, vz
       float acc[5][P];
       const float* const fp[5] = {p.f[5], p.f[6], p.f[7], p.f[8], p.f[9]};
-      SMK_GATHER(5, acc, sx2, sy2)
+      SMK_GATHER(5, acc, sx2, 0)
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         double xv, yv, zv;
@@ -317,7 +330,7 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
     } else {           // group B': eta_xz, eta_yz
       float acc[2][P];
       const float* const fp[2] = {p.f[5], p.f[6]};
-      SMK_GATHER(2, acc, sx2, sy2)
+      SMK_GATHER(2, acc, sx2, 0)
 #pragma unroll
       for (int k = 0; k < P; ++k) {
         double xv, yv, zv;
