@@ -331,21 +331,34 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
   //      (descending), both coalesced, and writes Z[k] = A + iB, Z[M-k] = conj(A) + i conj(B) with
   //      A = X[k] + conj(X[M-k]), B = (X[k] - conj(X[M-k])) w^-k.  The imaginary parts of the DC and Nyquist bins
   //      are ignored, as FFTW's / pocketfft's c2r do.
+  constexpr int KI = (M / 2 + 1 + 31) / 32;   // (k, M-k) pairs per lane and line
   for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
     const bool ok = line0 + line < p.nlines;
     const float2* src = p.in + (line0 + line) * p.pitch;
     float2* row = sm + line * LP;
-#pragma unroll 4
-    for (int k = threadIdx.x & 31; k <= M / 2; k += 32) {
-      float2 a = make_float2(0.f, 0.f), b = a;
-      if (ok) { a = __ldg(src + k); b = __ldg(src + M - k); }
-      if (k == 0) { a.y = 0.f; b.y = 0.f; }
-      float2 w = __ldg(p.tw + k);
-      w.y = -w.y;                                        // exp(+2 pi i k / NZ)
-      float2 A = make_float2(a.x + b.x, a.y - b.y);
-      float2 B = cmul(make_float2(a.x - b.x, a.y + b.y), w);
-      row[k] = make_float2(A.x - B.y, A.y + B.x);        // A + iB
-      if (k != 0 && k != M - k) row[M - k] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
+    // all loads of the line first (2*KI independent 8-byte loads per lane in flight), arithmetic afterwards
+    float2 a[KI], b[KI], w[KI];
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = (threadIdx.x & 31) + 32 * i;
+      a[i] = b[i] = w[i] = make_float2(0.f, 0.f);
+      if (k <= M / 2) {
+        w[i] = __ldg(p.tw + k);
+        if (ok) { a[i] = __ldg(src + k); b[i] = __ldg(src + M - k); }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const int k = (threadIdx.x & 31) + 32 * i;
+      if (k <= M / 2) {
+        float2 av = a[i], bv = b[i];
+        if (k == 0) { av.y = 0.f; bv.y = 0.f; }
+        const float2 wc = make_float2(w[i].x, -w[i].y);   // exp(+2 pi i k / NZ)
+        const float2 A = make_float2(av.x + bv.x, av.y - bv.y);
+        const float2 B = cmul(make_float2(av.x - bv.x, av.y + bv.y), wc);
+        row[k] = make_float2(A.x - B.y, A.y + B.x);        // A + iB
+        if (k != 0 && k != M - k) row[M - k] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
+      }
     }
   }
   __syncthreads();
