@@ -11,6 +11,7 @@
 //     sum of squares (for sigma) into the store, the forward fuses Philox noise into the load.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "smk_fft.cuh"
 #include "smk_internal.h"
@@ -49,6 +50,7 @@ struct StridedParams {
   // peer mode (fused exchange): output point k goes to rank k / aout.nsplit, into peer[rank] (that rank's receive
   // buffer, already offset to this rank's chunk) at (k % nsplit) * lo_stride + outer * outer_stride + column
   float2* peer[SMK_MAX_RANKS];
+  int pf_dist;   // L2 prefetch distance in tiles (0 = off): each CTA prefetches the input rows of tile id + pf_dist
 };
 
 // element offset of point n: plain stride, or the two-level [hi][lo] form left behind by an all-to-all
@@ -79,6 +81,20 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
                                             : (long long)col;
   const float2* __restrict__ inl = p.in + (outer * p.ain.outer_stride + in_col);
   float2* __restrict__ outl = p.out + (outer * p.aout.outer_stride + col);
+  if (!SPLIT_IN && p.pf_dist > 0) {
+    // The first stage exposes one full DRAM latency per CTA (60 % of the kernel in the ncu source view).  Pull the
+    // rows (one 128-B line each when LINES == 16) of the tile a later CTA will read into L2 now.
+    const long long id = (long long)blockIdx.y * gridDim.x + blockIdx.x + p.pf_dist;
+    const int ty = (int)(id / gridDim.x), tx = (int)(id - (long long)ty * gridDim.x);
+    if (ty < (int)gridDim.y) {
+      const float2* nxt = p.in + ((long long)ty * p.ain.outer_stride + (long long)tx * LINES);
+      for (int n = threadIdx.x; n < N; n += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + n * p.ain.lo_stride));
+      if (MUL == MUL_TABLE) {
+        const float* wn = p.mul.wt + ((long long)ty * p.mul.wt_outer_stride + min(tx * LINES, p.wcols - 1));
+        for (int n = threadIdx.x; n < N; n += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(wn + n * p.mul.wt_n_stride));
+      }
+    }
+  }
 
   // ---- fused multiply of make_boxes.py:247-429 (reference float32 rounding order), applied to the loaded element
   float wv[MUL == MUL_TABLE ? TPT0 : 1][MUL == MUL_TABLE ? R0 : 1];
@@ -203,6 +219,17 @@ static int launch_strided_n(bool inv, int mul, const StridedParams& p, int noute
 
 #define SMK_STRIDED_SIZES(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(2560)
 
+int prefetch_distance() {
+  static int d = -1;
+  if (d < 0) {
+    // tuning knob (tiles ahead).  Measured on B200 at 512 x 512 x 1536: no gain at any distance (y pass 0.645 ms
+    // without, 0.63-0.75 ms with; x pass with table 0.86 -> 1.13 ms), so the prefetch is off by default.
+    const char* e = getenv("SMK_PF_DIST");
+    d = e ? atoi(e) : 0;
+  }
+  return d;
+}
+
 int strided_tile_width(int n) {
 #define X(N_) if (n == N_) return StridedTraits<N_>::LINES;
   SMK_STRIDED_SIZES(X)
@@ -222,7 +249,7 @@ int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, floa
                        float2* const* peers, int npeers) {
   make_fastdiv(ain);
   make_fastdiv(aout);
-  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw, {nullptr}};
+  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw, {nullptr}, prefetch_distance()};
   if (peers) {
     if (npeers > SMK_MAX_RANKS) { set_error("too many ranks for the fused exchange"); return SMK_ERR_ARG; }
     for (int i = 0; i < npeers; ++i) p.peer[i] = peers[i];
@@ -318,6 +345,7 @@ struct C2RParams {
   const float2* tw;
   float norm;       // nx*ny*nz as float (the reference divides: box /= NX*NY*NZ)
   double* stats;    // [2] sum, sum of squares (atomically accumulated) or null
+  int pf_dist;      // L2 prefetch distance in tiles (0 = off)
 };
 
 template <int M>
@@ -331,6 +359,14 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
   //      (descending), both coalesced, and writes Z[k] = A + iB, Z[M-k] = conj(A) + i conj(B) with
   //      A = X[k] + conj(X[M-k]), B = (X[k] - conj(X[M-k])) w^-k.  The imaginary parts of the DC and Nyquist bins
   //      are ignored, as FFTW's / pocketfft's c2r do.
+  if (p.pf_dist > 0) {
+    const long long l0 = ((long long)blockIdx.x + p.pf_dist) * LINES;
+    if (l0 + LINES <= p.nlines) {
+      const char* nxt = reinterpret_cast<const char*>(p.in + l0 * p.pitch);
+      const int nline128 = LINES * p.pitch * 8 / 128;
+      for (int i = threadIdx.x; i < nline128; i += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128LL * i));
+    }
+  }
   constexpr int KI = (M / 2 + 1 + 31) / 32;   // (k, M-k) pairs per lane and line
   for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
     const bool ok = line0 + line < p.nlines;
@@ -454,7 +490,7 @@ static int launch_c2r_t(const C2RParams& p, cudaStream_t st) {
 
 int launch_c2r_z(int NZ, const float2* in, float* out, long long nlines, int pitch, const float2* tw, float norm,
                  double* stats, cudaStream_t st) {
-  C2RParams p{in, out, nlines, pitch, tw, norm, stats};
+  C2RParams p{in, out, nlines, pitch, tw, norm, stats, prefetch_distance() * 2 / 3};
   switch (NZ / 2) {
 #define X(M_) case M_: return launch_c2r_t<M_>(p, st);
     SMK_Z_HALF_SIZES(X)

@@ -88,6 +88,7 @@ struct PkParams {
 };
 int launch_pk_weights(const PkParams& p, cudaStream_t st);
 
+int prefetch_distance();
 bool strided_size_supported(int n);
 int strided_tile_width(int n);   // kz columns per tile of the strided pass of length n
 bool z_size_supported(int nz);
