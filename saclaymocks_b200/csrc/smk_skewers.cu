@@ -403,6 +403,7 @@ extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const f
                            const int* npix_forest, const double* rvec, int npix, float* delta_l, float* eta_par,
                            float* vpar) {
   using namespace smk;
+  if (nqso == 0 || npix == 0) return SMK_OK;     // empty catalogue: nothing to do (empty tensors have null pointers)
   if (!g || !fields || !fields[0] || !delta_l || (nqso > 0 && (!qso_xyzr || !npix_forest || !rvec))) {
     set_error("smk_skewers: null argument");
     return SMK_ERR_ARG;

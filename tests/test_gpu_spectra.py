@@ -210,3 +210,42 @@ def test_register_blocked_kernel_equals_simple_kernel(cuda, golden_ref32, monkey
         m = ~np.isnan(a)
         assert m.sum() > 10000
         assert np.max(np.abs(a[m] - b[m])) < tol
+
+
+def test_edge_cases_empty_and_out_of_range(cuda, golden_small):
+    """Empty catalogue, quasars outside [zmin, zmax] (make_spectra.py:437-438), a sightline outside the slab."""
+    from saclaymocks_b200 import spectra as sp
+    g = golden_small
+    geom = sp.SkewerGeometry(int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"]))
+    eng = sp.SkewerEngine(geom, device=cuda)
+    f = {k: torch.as_tensor(g["box_" + k], device=cuda) for k in sp.FIELDS}
+    out = eng.read_spec(f, np.zeros((0, 4)), np.zeros(0, dtype=np.int32))
+    assert out[0].shape == (0, geom.npixeltot)
+    xyzr, nfor = sp.qso_lines_of_sight(geom, np.float32([190.0, 190.1, 190.0]), np.float32([0.0, 0.1, 0.0]),
+                                       np.float32([1.5, 2.5, 3.9]), 190.0, 0.0)
+    assert list(nfor < 0) == [True, False, True]                      # z outside [1.8, 3.6] is dropped by the caller
+    # a slab that the sightline never enters leaves every pixel untouched (NaN initialisation)
+    d, e, v = eng.read_spec(f, xyzr[1:2], nfor[1:2], xmin=geom.LX / 2 - 1.0, xmax=geom.LX / 2)
+    assert bool(torch.isnan(d).all())
+    # forest length 0: owned pixels get the sentinels of make_spectra.py:99-101
+    d, e, v = eng.read_spec(f, xyzr[1:2], np.int32([0]))
+    assert bool((d == -1e6).all()) and bool((e == 0).all()) and bool((v == 0).all())
+    fg = sp.FGPA(geom, zfix=2.4, device=cuda)
+    F = fg.flux(d, None, e)
+    assert bool((F == 1.0).all())                                     # exp(-a exp(b G (-1e6))) == 1
+
+
+def test_null_box_is_reported(cuda):
+    """make_boxes.py:100-105: an all-zero box raises."""
+    from saclaymocks_b200.boxes import BoxSynth
+    bs = BoxSynth(16, 16, 24, 8.0, device=cuda)
+    boxk = bs.draw_grf_boxk(seed=3)
+    zeros = torch.zeros((16, 16, 13), dtype=torch.float32, device=cuda)
+    box, stats = bs.synth(boxk, "boxln_1", wtable=zeros)
+    with pytest.raises(ValueError):
+        bs.sigma(stats)
+    W = {k: zeros.cpu().numpy() for k in ("Pln1", "Pln2", "Pln3", "P0")}
+    from saclaymocks_b200 import _lib
+    with pytest.raises(_lib.SmkError, match="null"):
+        bs.make_boxes_host(W, seed=3)
+    bs.close()
