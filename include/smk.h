@@ -68,10 +68,12 @@ int smk_set_stream(smk_ctx* ctx, void* stream);   /* later calls launch on this 
 
 /* ---- per-pass device timing for the roofline report (bench.py).  When enabled, CUDA events are recorded on the
  * ctx stream around every FFT pass kernel; smk_timing_collect synchronises the stream and returns, per pass
- * (0 r2c-z, 1 forward-y, 2 forward-x, 3 inverse-x [with the fused multiply], 4 inverse-y, 5 c2r-z), the summed
- * duration in ms and the number of launches since the last collect. */
+ * (0 r2c-z, 1 forward-y, 2 forward-x, 3 inverse-x [with the fused multiply], 4 inverse-y, 5 c2r-z, 6 forward z+y
+ * chained through L2, 7 inverse y+z chained through L2 [one interval per transform]), the summed duration in ms and
+ * the number of intervals since the last collect. */
+#define SMK_NPASSES 8
 int smk_timing_enable(smk_ctx* ctx, int on);
-int smk_timing_collect(smk_ctx* ctx, double ms_sum[6], int count[6]);
+int smk_timing_collect(smk_ctx* ctx, double ms_sum[SMK_NPASSES], int count[SMK_NPASSES]);
 
 /* ---- spectral weight table of one product on the GPU (replaces the interpolate_pk.py / merge_pk.py stage,
  * bin/interpolate_pk.py:17-26, 63-77): wtable[x][y_local][kz] = float32(sqrt(float32(max(S(|k|), 0)) / Vcell)) with S

@@ -53,14 +53,14 @@ class BoxSynth(object):
             pass
 
     # ------------------------------------------------------------------ per-pass device timing (bench.py roofline)
-    PASS_NAMES = ("r2c_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "c2r_z")
+    PASS_NAMES = ("r2c_z", "fwd_y", "fwd_x", "inv_x", "inv_y", "c2r_z", "fwd_zy", "inv_yz")
 
     def timing_enable(self, on=True):
         _lib.check(self.lib.smk_timing_enable(self.h, int(on)))
 
     def timing_collect(self):
-        ms = (C.c_double * 6)()
-        n = (C.c_int * 6)()
+        ms = (C.c_double * len(self.PASS_NAMES))()
+        n = (C.c_int * len(self.PASS_NAMES))()
         _lib.check(self.lib.smk_timing_collect(self.h, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.PASS_NAMES)}
 

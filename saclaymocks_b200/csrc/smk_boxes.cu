@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
   }
   auto ld_g = [&](int, int n, int i, int t) {
     if (MUL == MUL_TABLE) wv[i][t] = __ldg(wtl + n * p.mul.wt_n_stride);
+    // the plain inverse pass (y) reads data nobody reads again: evict-first keeps L2 for the chained z pass's slot
+    if (INV && MUL == MUL_NONE) return __ldcs(inl + point_off<SPLIT_IN>(p.ain, n));
     return inl[point_off<SPLIT_IN>(p.ain, n)];
   };
   auto pre = [&](int, int n, int i, int t, float2 v) {
@@ -346,6 +348,7 @@ struct C2RParams {
   float norm;       // nx*ny*nz as float (the reference divides: box /= NX*NY*NZ)
   double* stats;    // [2] sum, sum of squares (atomically accumulated) or null
   int pf_dist;      // L2 prefetch distance in tiles (0 = off)
+  int discard_in;   // chained mode: the input is an L2-resident scratch slot; drop its lines after reading (no write-back)
 };
 
 template <int M>
@@ -398,6 +401,14 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
     }
   }
   __syncthreads();
+  if (p.discard_in) {
+    // every read of this CTA's input rows has completed (values are in shared memory): the rows are dead, so tell L2
+    // to drop them instead of writing them back to HBM when they are evicted
+    const long long nl = p.nlines - line0 < LINES ? p.nlines - line0 : LINES;
+    const char* base = reinterpret_cast<const char*>(p.in + line0 * p.pitch);
+    const int n128 = (int)(nl * p.pitch * 8 / 128);
+    for (int i = threadIdx.x; i < n128; i += NT) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + 128LL * i) : "memory");
+  }
   dif_stages_smem<P, 0, P::S - 1, true, LINES, LP, 1, NT>(sm, p.tw, 2);
   dif_last_resort_smem<P, true, LINES, LP, 1, NT>(sm, p.tw, 2);
   // ---- store x[2n], x[2n+1] = z[n] / N, accumulate sum and sum of squares
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
         float2 z = sm[line * LP + n];
         z.x = fdiv_fast(z.x, p.norm, rnorm);
         z.y = fdiv_fast(z.y, p.norm, rnorm);
-        dst[n] = z;
+        __stcs(dst + n, z);            // written once, read much later: streaming store
         s1 += z.x + z.y;
         s2 += z.x * z.x + z.y * z.y;
       }
@@ -489,8 +500,8 @@ static int launch_c2r_t(const C2RParams& p, cudaStream_t st) {
 }
 
 int launch_c2r_z(int NZ, const float2* in, float* out, long long nlines, int pitch, const float2* tw, float norm,
-                 double* stats, cudaStream_t st) {
-  C2RParams p{in, out, nlines, pitch, tw, norm, stats, prefetch_distance() * 2 / 3};
+                 double* stats, cudaStream_t st, bool discard_in) {
+  C2RParams p{in, out, nlines, pitch, tw, norm, stats, prefetch_distance() * 2 / 3, discard_in ? 1 : 0};
   switch (NZ / 2) {
 #define X(M_) case M_: return launch_c2r_t<M_>(p, st);
     SMK_Z_HALF_SIZES(X)

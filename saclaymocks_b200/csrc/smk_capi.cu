@@ -1,6 +1,14 @@
 // C ABI of libsmk.so (include/smk.h): context, plans, and the box-synthesis entry points.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+
+#ifndef SMK_YZ_GROUP_DEFAULT
+#define SMK_YZ_GROUP_DEFAULT 0
+#endif
+#ifndef SMK_YZ_STREAMS_DEFAULT
+#define SMK_YZ_STREAMS_DEFAULT 2
+#endif
 
 #include <vector>
 
@@ -28,6 +36,12 @@ struct smk_ctx {
   float2* xbuf[4] = {nullptr, nullptr, nullptr, nullptr};
   float2* xpeer[4][SMK_MAX_RANKS] = {};
   bool xconnected[4] = {false, false, false, false};
+  // y<->z chaining through L2 (see chain_setup): planes per group (0 = off), internal streams, ring of scratch slots
+  int yz_group = 0, yz_streams = 0;
+  bool yz_discard = true;
+  float2* yz_scratch = nullptr;
+  cudaStream_t yz_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t yz_fork = nullptr, yz_join[4] = {nullptr, nullptr, nullptr, nullptr};
   // optional per-pass CUDA-event timing (smk_timing_*): events are recorded around every pass kernel
   bool timing = false;
   std::vector<cudaEvent_t> ev;       // pool
@@ -35,7 +49,8 @@ struct smk_ctx {
   size_t ev_used = 0;
 };
 
-enum { PASS_R2C_Z = 0, PASS_FWD_Y, PASS_FWD_X, PASS_INV_X, PASS_INV_Y, PASS_C2R_Z, PASS_COUNT };
+enum { PASS_R2C_Z = 0, PASS_FWD_Y, PASS_FWD_X, PASS_INV_X, PASS_INV_Y, PASS_C2R_Z, PASS_FWD_ZY, PASS_INV_YZ, PASS_COUNT };
+static_assert(PASS_COUNT == SMK_NPASSES, "include/smk.h: SMK_NPASSES");
 
 // record an event; `pass` names the kernel launched right after it (-1: closes the previous interval only)
 static void tmark(smk_ctx* c, int pass) {
@@ -80,6 +95,121 @@ static int make_ktable(int n, bool rfft, double dcell, float** dptr, size_t* byt
   return SMK_OK;
 }
 
+// ---- y<->z chaining through L2.  The y and z passes of one transform both work on whole x planes, so they can be run
+// plane group by plane group with the intermediate (one group of [ny][pitch] planes) in a small scratch slot that is
+// overwritten group after group and therefore stays resident in the 126 MB L2: the y pass's writes and the z pass's
+// reads never reach HBM, and a 3-D transform moves 16 B per real cell instead of 24.  Groups are issued round robin on
+// a few internal streams (each with its own slot) so that the tail of one group's kernels overlaps the next group's.
+// SMK_YZ_GROUP = planes per group (0 disables), SMK_YZ_STREAMS = 1..4, SMK_YZ_PERSIST = 1 pins the slots in L2 with an
+// access-policy window.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static int chain_setup(smk_ctx* c) {
+  int g = env_int("SMK_YZ_GROUP", SMK_YZ_GROUP_DEFAULT);
+  if (g <= 0) return SMK_OK;
+  if (g > c->nxl) g = c->nxl;
+  int ns = env_int("SMK_YZ_STREAMS", SMK_YZ_STREAMS_DEFAULT);
+  ns = ns < 1 ? 1 : (ns > 4 ? 4 : ns);
+  const size_t slot = (size_t)g * c->ny * c->pitch * sizeof(float2);
+  SMK_CUDA_OK(cudaMalloc(&c->yz_scratch, slot * ns));
+  c->bytes += slot * ns;
+  SMK_CUDA_OK(cudaEventCreateWithFlags(&c->yz_fork, cudaEventDisableTiming));
+  for (int s = 0; s < ns; ++s) {
+    SMK_CUDA_OK(cudaStreamCreateWithFlags(&c->yz_stream[s], cudaStreamNonBlocking));
+    SMK_CUDA_OK(cudaEventCreateWithFlags(&c->yz_join[s], cudaEventDisableTiming));
+  }
+  if (env_int("SMK_YZ_PERSIST", 0)) {
+    int dev = 0, maxwin = 0, maxpersist = 0;
+    SMK_CUDA_OK(cudaGetDevice(&dev));
+    SMK_CUDA_OK(cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    SMK_CUDA_OK(cudaDeviceGetAttribute(&maxpersist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    size_t want = slot * ns;
+    if (want > (size_t)maxpersist) want = (size_t)maxpersist;
+    SMK_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    for (int s = 0; s < ns; ++s) {
+      cudaStreamAttrValue v{};
+      v.accessPolicyWindow.base_ptr = (char*)c->yz_scratch + slot * s;
+      v.accessPolicyWindow.num_bytes = slot < (size_t)maxwin ? slot : (size_t)maxwin;
+      v.accessPolicyWindow.hitRatio = 1.0f;
+      v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      SMK_CUDA_OK(cudaStreamSetAttribute(c->yz_stream[s], cudaStreamAttributeAccessPolicyWindow, &v));
+    }
+  }
+  c->yz_group = g;
+  c->yz_streams = ns;
+  c->yz_discard = env_int("SMK_YZ_DISCARD", 1) != 0;
+  return SMK_OK;
+}
+
+static int chain_fork(smk_ctx* c) {
+  SMK_CUDA_OK(cudaEventRecord(c->yz_fork, c->stream));
+  for (int s = 0; s < c->yz_streams; ++s) SMK_CUDA_OK(cudaStreamWaitEvent(c->yz_stream[s], c->yz_fork, 0));
+  return SMK_OK;
+}
+
+static int chain_join(smk_ctx* c) {
+  for (int s = 0; s < c->yz_streams; ++s) {
+    SMK_CUDA_OK(cudaEventRecord(c->yz_join[s], c->yz_stream[s]));
+    SMK_CUDA_OK(cudaStreamWaitEvent(c->stream, c->yz_join[s], 0));
+  }
+  return SMK_OK;
+}
+
+// inverse: y pass (input addressing `ain`, outer = local x plane) -> slot -> z pass -> out_slab
+static int chain_inverse_yz(smk_ctx* c, const float2* in, PassAddr ain, float* out_slab, double* stats) {
+  const int G = c->yz_group;
+  const size_t slot_elems = (size_t)G * c->ny * c->pitch;
+  const float norm = (float)((double)c->nx * c->ny * c->nz);
+  PassAddr aout{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
+  MulArgs m{};
+  tmark(c, PASS_INV_YZ);
+  int rc = chain_fork(c);
+  for (int x0 = 0, g = 0; x0 < c->nxl && rc == SMK_OK; x0 += G, ++g) {
+    const int n = c->nxl - x0 < G ? c->nxl - x0 : G;
+    const int s = g % c->yz_streams;
+    float2* slot = c->yz_scratch + slot_elems * s;
+    rc = launch_c2c_strided(c->ny, true, MUL_NONE, in + (long long)x0 * ain.outer_stride, slot, ain, aout, n, c->pitch,
+                            c->nzh, m, c->tw_y, c->yz_stream[s]);
+    if (rc) break;
+    rc = launch_c2r_z(c->nz, slot, out_slab + (size_t)x0 * c->ny * c->nz, (long long)n * c->ny, c->pitch, c->tw_z, norm,
+                      stats, c->yz_stream[s], c->yz_discard);
+  }
+  if (rc) return rc;
+  rc = chain_join(c);
+  tmark(c, -1);
+  return rc;
+}
+
+// forward: z pass (noise or box_slab) -> slot -> y pass -> `out` with addressing `aout`
+static int chain_forward_zy(smk_ctx* c, const float* box_slab, uint64_t seed, float2* out, PassAddr aout) {
+  const int G = c->yz_group;
+  const size_t slot_elems = (size_t)G * c->ny * c->pitch;
+  const long long cell0 = (long long)c->rank * c->nxl * c->ny * c->nz;
+  PassAddr ain{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
+  MulArgs m{};
+  tmark(c, PASS_FWD_ZY);
+  int rc = chain_fork(c);
+  for (int x0 = 0, g = 0; x0 < c->nxl && rc == SMK_OK; x0 += G, ++g) {
+    const int n = c->nxl - x0 < G ? c->nxl - x0 : G;
+    const int s = g % c->yz_streams;
+    float2* slot = c->yz_scratch + slot_elems * s;
+    const size_t off = (size_t)x0 * c->ny * c->nz;
+    rc = launch_r2c_z(c->nz, box_slab ? box_slab + off : nullptr, slot, (long long)n * c->ny, c->pitch, c->tw_z,
+                      box_slab == nullptr, seed, cell0 + (long long)off, c->yz_stream[s]);
+    if (rc) break;
+    rc = launch_c2c_strided(c->ny, false, MUL_NONE, slot, out + (long long)x0 * aout.outer_stride, ain, aout, n, c->pitch,
+                            c->nzh, m, c->tw_y, c->yz_stream[s]);
+  }
+  if (rc) return rc;
+  rc = chain_join(c);
+  tmark(c, -1);
+  return rc;
+}
+
 extern "C" {
 
 const char* smk_last_error(void) { return g_err.c_str(); }
@@ -116,6 +246,7 @@ int smk_ctx_create(smk_ctx** out, int nx, int ny, int nz, double dcell, int rank
   SMK_CUDA_OK(cudaMalloc(&c->work, wbytes));
   c->bytes += wbytes;
   SMK_CUDA_OK(cudaMalloc(&c->stats, 2 * SMK_NPRODUCTS * sizeof(double)));
+  if ((rc = chain_setup(c))) return rc;
   *out = c;
   return SMK_OK;
 }
@@ -124,7 +255,12 @@ int smk_ctx_destroy(smk_ctx* c) {
   if (!c) return SMK_OK;
   cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->tw_z);
   cudaFree(c->kx); cudaFree(c->ky); cudaFree(c->kz);
-  cudaFree(c->work); cudaFree(c->stats);
+  cudaFree(c->work); cudaFree(c->stats); cudaFree(c->yz_scratch);
+  if (c->yz_fork) cudaEventDestroy(c->yz_fork);
+  for (int s = 0; s < 4; ++s) {
+    if (c->yz_join[s]) cudaEventDestroy(c->yz_join[s]);
+    if (c->yz_stream[s]) cudaStreamDestroy(c->yz_stream[s]);
+  }
   for (int b = 0; b < c->nxbuf; ++b) {
     for (int r = 0; r < c->nranks; ++r)
       if (c->xconnected[b] && r != c->rank && c->xpeer[b][r]) cudaIpcCloseMemHandle(c->xpeer[b][r]);
@@ -162,7 +298,7 @@ int smk_timing_enable(smk_ctx* c, int on) {
   return SMK_OK;
 }
 
-int smk_timing_collect(smk_ctx* c, double ms_sum[6], int count[6]) {
+int smk_timing_collect(smk_ctx* c, double ms_sum[SMK_NPASSES], int count[SMK_NPASSES]) {
   for (int i = 0; i < PASS_COUNT; ++i) { ms_sum[i] = 0.0; count[i] = 0; }
   SMK_CUDA_OK(cudaStreamSynchronize(c->stream));
   for (size_t i = 0; i + 1 < c->ev_used; ++i) {
@@ -187,6 +323,10 @@ int smk_fft_r2c_local(smk_ctx* c, const float* box_slab, uint64_t seed, void* se
   long long nlines = (long long)c->nxl * c->ny;
   long long cell0 = (long long)c->rank * nlines * c->nz;
   float2* tmp = (c->nranks == 1) ? (float2*)sendbuf : c->work;
+  if (c->yz_group > 0) {
+    PassAddr aout{(long long)c->nyl * c->pitch, (long long)c->nxl * c->nyl * c->pitch, (long long)c->pitch, c->nyl};
+    return chain_forward_zy(c, box_slab, seed, (float2*)sendbuf, aout);
+  }
   tmark(c, PASS_R2C_Z);
   int rc = launch_r2c_z(c->nz, box_slab, tmp, nlines, c->pitch, c->tw_z, box_slab == nullptr, seed, cell0, c->stream);
   if (rc) return rc;
@@ -338,6 +478,7 @@ int smk_synth_c2r_finish_p2p(smk_ctx* c, int buf, float* out_slab, double* stats
   PassAddr ain{(long long)LX, chunk, (long long)c->nxl * LX, c->nyl};
   ain.tile_width = LX;
   ain.tile_stride = (long long)c->nyl * c->nxl * LX;
+  if (c->yz_group > 0) return chain_inverse_yz(c, c->xbuf[buf], ain, out_slab, stats);
   PassAddr aout{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
   MulArgs m{};
   tmark(c, PASS_INV_Y);
@@ -354,6 +495,7 @@ int smk_synth_c2r_finish_p2p(smk_ctx* c, int buf, float* out_slab, double* stats
 int smk_synth_c2r_finish(smk_ctx* c, void* recvbuf, float* out_slab, double* stats) {
   // y pass: input [src][xl][yl][z] (y = src*nyl + yl), output [xl][ny][pitch]
   PassAddr ain{(long long)c->nyl * c->pitch, (long long)c->nxl * c->nyl * c->pitch, (long long)c->pitch, c->nyl};
+  if (c->yz_group > 0) return chain_inverse_yz(c, (const float2*)recvbuf, ain, out_slab, stats);
   PassAddr aout{(long long)c->ny * c->pitch, 0, (long long)c->pitch, c->ny};
   float2* tmp = (c->nranks == 1) ? (float2*)recvbuf : c->work;
   MulArgs m{};

@@ -73,7 +73,7 @@ int launch_r2c_z(int NZ, const float* in, float2* out, long long nlines, int pit
                  bool philox, uint64_t seed, long long cell0, cudaStream_t st);
 
 int launch_c2r_z(int NZ, const float2* in, float* out, long long nlines, int pitch, const float2* tw, float norm,
-                 double* stats, cudaStream_t st);
+                 double* stats, cudaStream_t st, bool discard_in = false);
 
 int launch_philox_fill(float* out, long long ncells, uint64_t seed, long long cell0, cudaStream_t st);
 

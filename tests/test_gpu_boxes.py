@@ -47,6 +47,26 @@ def test_boxes_match_oracle(cuda, shape, dcell):
     bs.close()
 
 
+@pytest.mark.parametrize("group,streams", [(1, 1), (3, 2), (8, 3), (64, 2)])
+def test_boxes_chained_yz_match_oracle(cuda, monkeypatch, group, streams):
+    """y<->z passes chained through an L2-resident scratch slot (plane groups on internal streams, ragged last
+    group, L2 discard of the dead slot lines): same results as the oracle, forward and inverse."""
+    from saclaymocks_b200.boxes import BoxSynth, PRODUCTS, WEIGHT_OF
+    monkeypatch.setenv("SMK_YZ_GROUP", str(group))
+    monkeypatch.setenv("SMK_YZ_STREAMS", str(streams))
+    NX, NY, NZ, dcell = 32, 64, 96, 4.0
+    W, noise, raw, p0, boxes, sig = _oracle_run(NX, NY, NZ, dcell, 42)
+    bs = BoxSynth(NX, NY, NZ, dcell, device=cuda)
+    boxk = bs.draw_grf_boxk(noise=torch.as_tensor(noise, device=cuda))
+    assert rel_l2(bs.boxk_to_numpy(boxk), raw) < TOL
+    Wd = {k: bs.upload_weights(v) for k, v in W.items()}
+    for name in PRODUCTS:
+        box, stats = bs.synth(boxk, name, wtable=Wd.get(WEIGHT_OF.get(name)))
+        assert rel_l2(box.cpu().numpy(), boxes[name]) < TOL, name
+        assert abs(bs.sigma(stats) / sig[name] - 1) < 1e-4, name
+    bs.close()
+
+
 def test_boxes_match_reference_golden(cuda, golden_small):
     """16 x 16 x 96 run of the unmodified reference make_boxes.py (tests/golden/ref_small.npz)."""
     from oracle import boxes as ob

@@ -19,4 +19,7 @@ for name, wt in (("eta_xy", None), ("boxln_1", W)):
     t = bs.timing_collect()
     bs.timing_enable(False)
     nk = NX * NY * (NZ // 2 + 1) * 8
-    print(os.environ.get("SMK_LIB_PATH", "default"), name, {k: "%.3f ms %.0f GB/s" % (ms / n, 2 * nk / (ms / n * 1e-3) / 1e9) for k, (ms, n) in t.items() if n})
+    mult = {"inv_yz": 4, "fwd_zy": 3}      # chained pairs: bytes of both passes under the 24 B/cell model
+    tot = sum(ms / n for ms, n in t.values() if n)
+    print(os.environ.get("SMK_YZ_GROUP", "0"), os.environ.get("SMK_YZ_STREAMS", "-"), name, "total %.3f ms" % tot,
+          {k: "%.3f ms %.0f GB/s" % (ms / n, mult.get(k, 2) * nk / (ms / n * 1e-3) / 1e9) for k, (ms, n) in t.items() if n})
