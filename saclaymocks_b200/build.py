@@ -41,5 +41,17 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(tag, defines):
+    """Kernel-tuning helper: libsmk_<tag>.so compiled with extra -D flags (select it with SMK_LIB_PATH)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = [f for f in FLAGS if not f.startswith("--use_fast_math")] + ["-D" + d for d in defines]
+    out = os.path.join(HERE, "libsmk_%s.so" % tag)
+    subprocess.check_call([nvcc] + flags + ["-shared", "-o", out] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart"])
+    return out
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

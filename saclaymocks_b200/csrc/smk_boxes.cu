@@ -64,8 +64,15 @@ __device__ __forceinline__ long long point_off(const PassAddr& a, int n) {
 
 enum { OUT_PLAIN = 0, OUT_SPLIT = 1, OUT_PEER = 2 };
 
+// Fused-multiply x passes (measured at 512 x 512 x 1536, tools/x_sweep.sh): the k-factor variants (eta, velocity) load
+// their first-stage tasks two at a time, which fits 80 registers = 3 CTAs per SM (0.738 -> 0.702 ms); the table variant
+// needs the weights as well, spills at 80 registers (0.870 -> 0.914 ms) and keeps all loads in flight at 2 CTAs per SM.
+#ifndef SMK_MUL_BATCH
+#define SMK_MUL_BATCH 2   // first-stage tasks loaded together in the k-factor passes (0 = all)
+#endif
+
 template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
-__global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || StridedTraits<N>::MINB == 1)
+__global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL != MUL_TABLE || StridedTraits<N>::MINB == 1)
                                                               ? StridedTraits<N>::MINB
                                                               : StridedTraits<N>::MINB - 1)
     c2c_strided_kernel(const __grid_constant__ StridedParams p) {
@@ -73,7 +80,9 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
   constexpr int LINES = StridedTraits<N>::LINES;
   constexpr int NT = StridedTraits<N>::NT;
   constexpr int R0 = P::radix(0);
-  constexpr int TPT0 = (N / R0 * LINES + NT - 1) / NT;
+  constexpr int TPT0_ALL = (N / R0 * LINES + NT - 1) / NT;
+  constexpr int B0 = (MUL == MUL_NONE || MUL == MUL_TABLE || P::S == 1) ? 0 : SMK_MUL_BATCH;   // first-stage batch
+  constexpr int TPT0 = (B0 > 0 && B0 < TPT0_ALL) ? B0 : TPT0_ALL;
   extern __shared__ float2 sm[];   // [N][LINES]
   const int col = blockIdx.x * LINES + threadIdx.x % LINES;   // this thread's kz column (fixed for the kernel)
   const int outer = blockIdx.y;
@@ -150,7 +159,7 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
     if constexpr (P::S == 1) {
       dif_stage<P, 0, INV, LINES, NT, OUT_RESORT>(ld_g, st_s, p.tw, 1, pre);
     } else {
-      dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE>(ld_g, st_s, p.tw, 1, pre);
+      dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE, decltype(ld_g), decltype(st_s), decltype(pre), B0>(ld_g, st_s, p.tw, 1, pre);
       __syncthreads();
       dif_stages_smem<P, 1, P::S - 1, INV, LINES, 1, LINES, NT>(sm, p.tw, 1);
       dif_stage<P, P::S - 1, INV, LINES, NT, OUT_RESORT>(ld_s, st_s, p.tw, 1);
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL == MUL_NONE || Stri
   } else if constexpr (P::S == 1) {
     dif_stage<P, 0, INV, LINES, NT, OUT_NATURAL>(ld_g, st_g, p.tw, 1, pre);
   } else {
-    dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE>(ld_g, st_s, p.tw, 1, pre);
+    dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE, decltype(ld_g), decltype(st_s), decltype(pre), B0>(ld_g, st_s, p.tw, 1, pre);
     __syncthreads();
     dif_stages_smem<P, 1, P::S - 1, INV, LINES, 1, LINES, NT>(sm, p.tw, 1);
     dif_stage<P, P::S - 1, INV, LINES, NT, OUT_NATURAL>(ld_s, st_g, p.tw, 1);

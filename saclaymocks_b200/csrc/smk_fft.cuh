@@ -245,10 +245,11 @@ struct NoPre {
   __device__ __forceinline__ float2 operator()(int, int, int, int, float2 v) const { return v; }
 };
 
-// ld(line, pos, i, t): i = task slot of this thread, t = input index of the butterfly (both compile-time after
+// ld(line, pos, i, t): i = task slot of this thread within the current batch, t = input index of the butterfly (both compile-time after
 // unrolling, so a caller can keep per-element side data in a register array indexed [i][t]);
 // pre(line, pos, i, t, v) runs after ALL loads of the thread have been issued (fused multiply of the first stage).
-template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store, class Pre = NoPre>
+template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store, class Pre = NoPre,
+          int BATCH = 0>
 __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __restrict__ tw, int twmul,
                                           Pre pre = Pre()) {
   constexpr int R = P::radix(STAGE);
@@ -260,47 +261,54 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
   static_assert(OUT == OUT_INPLACE || LAST, "natural-order store only on the last stage");
   static_assert(NT % LINES == 0, "threads per block must be a multiple of the lines per tile");
   constexpr int TPT = (NTASK + NT - 1) / NT;
+  // tasks whose loads are issued together (default: all of the thread's tasks; a smaller batch trades loads in flight
+  // for registers, which lets the fused-multiply passes keep 3 CTAs per SM)
+  constexpr int TB = (BATCH > 0 && BATCH < TPT) ? BATCH : TPT;
+  static_assert(OUT != OUT_RESORT || TB == TPT, "a re-sorting stage reads everything before it writes");
   constexpr bool EVEN = (NTASK % NT == 0);
   constexpr int JSTEP = NT / LINES;
   // a thread always works on the same line: task = threadIdx.x + i*NT  =>  line = threadIdx.x % LINES
   const int line = threadIdx.x % LINES;
   const int j0 = threadIdx.x / LINES;
-  // phase 1: all loads of this thread (keeps TPT*R independent loads in flight)
-  float2 v[TPT][R];
 #pragma unroll
-  for (int i = 0; i < TPT; ++i) {
-    const int j = j0 + i * JSTEP;
-    if (EVEN || j < NB) {
-      const int b = j / MQ, o = j - b * MQ;
+  for (int i0 = 0; i0 < TPT; i0 += TB) {
+    // phase 1: the loads of this batch (keeps TB*R independent loads in flight)
+    float2 v[TB][R];
 #pragma unroll
-      for (int t = 0; t < R; ++t) v[i][t] = ld(line, b * M + o + t * MQ, i, t);
-    }
-  }
-  if (OUT == OUT_RESORT) __syncthreads();
+    for (int ii = 0; ii < TB; ++ii) {
+      const int j = j0 + (i0 + ii) * JSTEP;
+      if (i0 + ii < TPT && (EVEN || j < NB)) {
+        const int b = j / MQ, o = j - b * MQ;
 #pragma unroll
-  for (int i = 0; i < TPT; ++i) {
-    const int j = j0 + i * JSTEP;
-    if (EVEN || j < NB) {
-      const int b = j / MQ, o = j - b * MQ;
-#pragma unroll
-      for (int t = 0; t < R; ++t) v[i][t] = pre(line, b * M + o + t * MQ, i, t, v[i][t]);
-      Butterfly<R, INV>::run(v[i]);
-      if (!LAST) {
-        const int oc = o * ((P::N / M) * twmul);   // W_sub^(o q) = W_L[q * oc]
-#pragma unroll
-        for (int q = 1; q < R; ++q) {
-          float2 w = __ldg(tw + q * oc);
-          if (INV) w.y = -w.y;
-          v[i][q] = cmul(v[i][q], w);
-        }
+        for (int t = 0; t < R; ++t) v[ii][t] = ld(line, b * M + o + t * MQ, ii, t);
       }
-      if (OUT != OUT_INPLACE) {
-        const int nb = P::nat(b * M);
+    }
+    if (OUT == OUT_RESORT) __syncthreads();
 #pragma unroll
-        for (int q = 0; q < R; ++q) st(line, nb + q * (P::N / R), v[i][q]);
-      } else {
+    for (int ii = 0; ii < TB; ++ii) {
+      const int j = j0 + (i0 + ii) * JSTEP;
+      if (i0 + ii < TPT && (EVEN || j < NB)) {
+        const int b = j / MQ, o = j - b * MQ;
 #pragma unroll
-        for (int q = 0; q < R; ++q) st(line, b * M + o + q * MQ, v[i][q]);
+        for (int t = 0; t < R; ++t) v[ii][t] = pre(line, b * M + o + t * MQ, ii, t, v[ii][t]);
+        Butterfly<R, INV>::run(v[ii]);
+        if (!LAST) {
+          const int oc = o * ((P::N / M) * twmul);   // W_sub^(o q) = W_L[q * oc]
+#pragma unroll
+          for (int q = 1; q < R; ++q) {
+            float2 w = __ldg(tw + q * oc);
+            if (INV) w.y = -w.y;
+            v[ii][q] = cmul(v[ii][q], w);
+          }
+        }
+        if (OUT != OUT_INPLACE) {
+          const int nb = P::nat(b * M);
+#pragma unroll
+          for (int q = 0; q < R; ++q) st(line, nb + q * (P::N / R), v[ii][q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < R; ++q) st(line, b * M + o + q * MQ, v[ii][q]);
+        }
       }
     }
   }

@@ -34,7 +34,30 @@ struct SkewerParams {
   float* delta_l;
   float* eta_par;
   float* vpar;
+  int pf;                  // tuning: 0 none, 1 = L2 prefetch of the next x slab of the window, 2 = L1 prefetch of the next row, 3 = both
 };
+
+// Blackwell packed FP32: one FFMA2 / FMUL2 issues two fused multiply-adds (fma.rn.f32x2, sm_100+)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 
 template <int DMAX, int NF>
 __device__ __forceinline__ void gather(const SkewerParams& p, int ixl, int iy, int iz, const float (&wx)[2 * DMAX + 1],
@@ -192,6 +215,82 @@ __device__ __forceinline__ void gather_multi(const SkewerParams& p, const float*
   }
 }
 
+// Same walk with packed arithmetic: the z contraction runs on pairs of cells (4 FMUL2/FFMA2 + one add per pixel and
+// row instead of 8 FFMA) and the row accumulation on pairs of pixels (P/2 FFMA2 instead of P FFMA): 30 instead of 44
+// issue slots per (row, field) at P = 4.  wz2[q][j] = (wz[q][2j], wz[q][2j+1]); acc2[f][h] = pixels (2h, 2h+1).
+template <int DMAX, int P, int NF, bool INTERIOR>
+__device__ __forceinline__ void gather_multi2(const SkewerParams& p, const float* const (&fp)[NF], int bx, int by,
+                                              int bz, int nxu, int nyu, const int (&dix)[P], const float (&ox)[P],
+                                              const float* wy_s, const float2 (&wz2)[P][DMAX + 1], float inv_sig2,
+                                              float2 (&acc2)[NF][P / 2], float (&sx)[P]) {
+  constexpr int WU = 2 * DMAX + 2;
+  static_assert(P % 2 == 0, "packed gather works on pixel pairs");
+  const float fdx = (float)p.dx;
+#pragma unroll
+  for (int f = 0; f < NF; ++f)
+#pragma unroll
+    for (int h = 0; h < P / 2; ++h) acc2[f][h] = make_float2(0.f, 0.f);
+  int lz[WU];
+#pragma unroll
+  for (int c = 0; c < WU; ++c) lz[c] = INTERIOR ? c : min(max(bz - DMAX + c, 0), p.nz - 1);
+  const int z0 = INTERIOR ? bz - DMAX : 0;
+#pragma unroll
+  for (int q = 0; q < P; ++q) sx[q] = 0.f;
+  const unsigned plane = (unsigned)p.ny * (unsigned)p.nz;
+  for (int a = 0; a < nxu; ++a) {
+    const int la = INTERIOR ? (bx - DMAX + a - p.ix0) : min(max(bx - DMAX + a - p.ix0, 0), p.nxs - 1);
+    if (INTERIOR && (p.pf & 1) && a + 1 < nxu) {
+      // the rows of the next x slab of the window are known now and needed ~8 row iterations from now: pull the
+      // sector at the centre of each into L2 (the loads of a row otherwise expose one DRAM latency per iteration)
+      const size_t nrow = (size_t)(la + 1) * plane + (unsigned)(by - DMAX) * (unsigned)p.nz + z0 + DMAX;
+      for (int b = 0; b < nyu; ++b)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp[f] + nrow + (size_t)b * p.nz));
+    }
+    float wxa[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      const int m = a - DMAX - dix[q];
+      const float t = m * fdx + ox[q];
+      wxa[q] = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
+      sx[q] += wxa[q];
+    }
+    for (int b = 0; b < nyu; ++b) {
+      const int lb = INTERIOR ? (by - DMAX + b) : min(max(by - DMAX + b, 0), p.ny - 1);
+      if (INTERIOR && (p.pf & 2) && b + 1 < nyu) {
+        const size_t nrow = (size_t)la * plane + (unsigned)(lb + 1) * (unsigned)p.nz + z0;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow + WU - 1));
+        }
+      }
+      float2 wab2[P / 2];
+#pragma unroll
+      for (int h = 0; h < P / 2; ++h)
+        wab2[h] = make_float2(wxa[2 * h] * wy_s[(b * P + 2 * h) * 128], wxa[2 * h + 1] * wy_s[(b * P + 2 * h + 1) * 128]);
+      const size_t row = (size_t)la * plane + (unsigned)lb * (unsigned)p.nz + z0;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const float* __restrict__ src = fp[f] + row;
+        float2 r2[WU / 2];
+#pragma unroll
+        for (int j = 0; j < WU / 2; ++j) r2[j] = make_float2(__ldg(src + lz[2 * j]), __ldg(src + lz[2 * j + 1]));
+#pragma unroll
+        for (int h = 0; h < P / 2; ++h) {
+          float2 s0 = fmul2(wz2[2 * h][0], r2[0]), s1 = fmul2(wz2[2 * h + 1][0], r2[0]);
+#pragma unroll
+          for (int j = 1; j < WU / 2; ++j) {
+            s0 = ffma2(wz2[2 * h][j], r2[j], s0);
+            s1 = ffma2(wz2[2 * h + 1][j], r2[j], s1);
+          }
+          acc2[f][h] = ffma2(wab2[h], make_float2(s0.x + s0.y, s1.x + s1.y), acc2[f][h]);
+        }
+      }
+    }
+  }
+}
+
 template <int DMAX, int P>
 __device__ __forceinline__ void pixel_xyz(const SkewerParams& p, int q, int i, double& xv, double& yv, double& zv) {
   const double R = p.qso[4 * q + 3], r = p.rvec[i];
@@ -200,7 +299,7 @@ __device__ __forceinline__ void pixel_xyz(const SkewerParams& p, int q, int i, d
   zv = r * p.qso[4 * q + 2] / R;
 }
 
-template <int DMAX, int P, int MINB>
+template <int DMAX, int P, int MINB, bool F2>
 __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_constant__ SkewerParams p, int nchunk) {
   constexpr int WU = 2 * DMAX + 2;
   const int q = blockIdx.x / nchunk;
@@ -259,6 +358,11 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
       sz[k] += wz[k][c];
     }
   }
+  float2 wz2[P][DMAX + 1];      // packed copy for the FFMA2 path (dead code otherwise)
+#pragma unroll
+  for (int k = 0; k < P; ++k)
+#pragma unroll
+    for (int j = 0; j <= DMAX; ++j) wz2[k][j] = make_float2(wz[k][2 * j], wz[k][2 * j + 1]);
   // y weights of the union window, once per thread, shared by the two field-group passes: [b][q][thread]
   __shared__ float s_wy[(2 * DMAX + 2) * P * 128];
   float* wy_s = s_wy + threadIdx.x;
@@ -288,8 +392,19 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
 #pragma unroll
   for (int k = 0; k < P; ++k) { eta[k] = 0.0; vel[k] = 0.0; }
 #define SMK_GATHER(NF_, ACC, SX, SY_UNUSED)                                                                              \
-  if (interior) gather_multi<DMAX, P, NF_, true>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz, inv_sig2, ACC, SX);    \
-  else gather_multi<DMAX, P, NF_, false>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz, inv_sig2, ACC, SX);
+  if constexpr (F2) {                                                                                                    \
+    float2 acc2_[NF_][P / 2];                                                                                            \
+    if (interior) gather_multi2<DMAX, P, NF_, true>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz2, inv_sig2, acc2_, SX); \
+    else gather_multi2<DMAX, P, NF_, false>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz2, inv_sig2, acc2_, SX);       \
+    _Pragma("unroll") for (int f_ = 0; f_ < NF_; ++f_)                                                                   \
+      _Pragma("unroll") for (int h_ = 0; h_ < P / 2; ++h_) {                                                             \
+        ACC[f_][2 * h_] = acc2_[f_][h_].x;                                                                               \
+        ACC[f_][2 * h_ + 1] = acc2_[f_][h_].y;                                                                           \
+      }                                                                                                                  \
+  } else {                                                                                                               \
+    if (interior) gather_multi<DMAX, P, NF_, true>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz, inv_sig2, ACC, SX);  \
+    else gather_multi<DMAX, P, NF_, false>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz, inv_sig2, ACC, SX);          \
+  }
   if (NFI == 1) {
     float acc[1][P];
     const float* const fp[1] = {p.f[0]};
@@ -353,13 +468,13 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
   }
 }
 
-template <int P, int MINB>
+template <int P, int MINB, bool F2 = false>
 static int launch_multi(const SkewerParams& p, cudaStream_t st) {
   const int NT = 128;
   int nchunk = (p.npix + NT * P - 1) / (NT * P);
   long long nblocks = (long long)nchunk * p.nqso;
   if (nblocks > 2147483647LL) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
-  skewers_multi_kernel<3, P, MINB><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk);
+  skewers_multi_kernel<3, P, MINB, F2><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk);
   SMK_CUDA_OK(cudaGetLastError());
   return SMK_OK;
 }
@@ -369,16 +484,21 @@ int launch_skewers(const SkewerParams& p, int dmax, double pixel_step, cudaStrea
   const int NT = 128;
   // register-blocked kernel: valid while P consecutive pixels cannot cross two cell boundaries on any axis
   const double cell = fmin(p.dx, fmin(p.dy, p.dz));
-  int variant = SMK_SKEW_P;
-  const char* env = getenv("SMK_SKEW_VARIANT");      // tuning knob: pixels per thread (2, 3, 4) or 44 (4 px, 4 CTAs/SM)
+  // default: 4 pixels per thread, packed FFMA2 arithmetic, 3 CTAs per SM (measured on B200 at 512 x 512 x 1536, whole
+  // skewer stage: plain FFMA 18.4 ms, FFMA2 17.6-17.8 ms, FFMA2 + L1 prefetch of the next row 16.6 ms)
+  int variant = 42;
+  const char* env = getenv("SMK_SKEW_VARIANT");      // tuning knob: pixels per thread (2, 3, 4), 44 (4 px, 4 CTAs/SM),
+                                                     // 42 / 442 (4 px, FFMA2 arithmetic, 3 / 4 CTAs/SM)
   if (env) variant = atoi(env);
-  const int PB = variant == 44 ? 4 : variant;
+  const int PB = (variant == 44 || variant == 42 || variant == 442) ? 4 : variant;
   const bool multi = (dmax == 3) && pixel_step > 0 && (PB - 1) * pixel_step < cell;
   if (multi) {
     switch (variant) {
       case 2: return launch_multi<2, 5>(p, st);
       case 3: return launch_multi<3, 4>(p, st);
       case 44: return launch_multi<4, 4>(p, st);
+      case 42: return launch_multi<4, 3, true>(p, st);     // packed FFMA2 arithmetic
+      case 442: return launch_multi<4, 4, true>(p, st);
       default: return launch_multi<4, 3>(p, st);
     }
   }
@@ -425,6 +545,7 @@ extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const f
   p.nqso = nqso; p.npix = npix;
   p.qso = qso_xyzr; p.npix_forest = npix_forest; p.rvec = rvec;
   p.delta_l = delta_l; p.eta_par = eta_par; p.vpar = vpar;
+  { const char* e = getenv("SMK_SKEW_PF"); p.pf = e ? atoi(e) : 2; }
   // largest step between consecutive pixels of the grid (uniform 0.2 Mpc/h in the reference); decides whether the
   // register-blocked kernel may be used.  SMK_SKEWERS_SIMPLE=1 forces the one-pixel-per-thread kernel.
   double step = g->pixel_step;
