@@ -173,6 +173,47 @@ int smk_smallscale(smk_ctx* ctx, int nqso, int nfft, int npix, const float* nois
 int smk_fgpa(smk_ctx* ctx, int nqso, int npix, const float* delta_l, const float* delta_s, const float* eta_par,
              const float* growthf, const float* a, const float* b, const float* c, float* flux);
 
+/* ---- quasar drawing on device-resident boxes: the cell loop of bin/draw_qso.py for one
+ * x-slab -- ptot(z) from the three lognormal boxes (draw_qso.py:228-251), cond1 & cond2 & cond3, the random position
+ * inside the cell, (ra, dec) and the redshift-space shift of the quasar redshift (draw_qso.py:394-480).  All pointers
+ * are device pointers.  Boxes are float [nxs][ny][nz] slabs whose first plane is global plane ix0.  Tables (float64):
+ * x_axis/y_axis/z_axis = cell centres (draw_qso.py:208-210); chi/zt[ntab] = comoving distance (Mpc) and redshift of
+ * util.cosmo (r_2_z); coef_z/coef_v[ncoef] = util.qso_lognormal_coef; dn_cell = n(z) per cell on the grid
+ * dz_interp0 + i*delta_z (draw_qso.py:300-334); dg_z/dg_v[ndg] = etc/dgrowth.fits.  Scalars as computed by the host
+ * set-up (saclaymocks_b200/qso.py).  Uniform variates: u1,u2,uz [nz][nxs][ny], ux [nz][nxs], uy [nz][ny] (the
+ * reference's legacy NumPy stream, draw_qso.py:425-445) or all NULL to draw Philox4x32-10(seed, global cell).
+ * Output: counters[0] = number of quasars selected (may exceed `capacity`: then only the first `capacity` records
+ * were stored and the call must be repeated with a larger buffer), counters[1] = cells passing cond1; records
+ * [capacity][8] doubles: key = (plane*nxs + ix)*ny + iy, z, z_rsd, ra, dec (degrees), X, Y, Z (Mpc/h), in arbitrary
+ * order (sort by key for the reference's np.where order).  counters must be zeroed by the caller. */
+typedef struct smk_qso_params {
+  int nxs, ny, nz, ix0, nx_full;
+  const float* boxln[3];
+  const float* velo[3];
+  int rsd;
+  const double *x_axis, *y_axis, *z_axis;
+  double dx, dy, dz;
+  const double *chi, *zt;
+  int ntab;
+  const double *coef_z, *coef_v;
+  int ncoef;
+  const double* dn_cell;
+  double dz_interp0, delta_z;
+  const double *dg_z, *dg_v;
+  int ndg;
+  double dgrowth0, H0, h;
+  double z1, z2, z3;
+  double sigma_p[3];
+  double norm, density_max;
+  double z_min, z_max;
+  double ra0, dec0, dra, ddec;          /* degrees */
+  double cr0, sr0, cd0, sd0;            /* cos/sin of ra0, dec0 (radians), computed by the host like numpy */
+  const double *u1, *u2, *ux, *uy, *uz;
+  uint64_t seed;
+} smk_qso_params;
+
+int smk_draw_qso(smk_ctx* ctx, const smk_qso_params* p, int* counters, double* records, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

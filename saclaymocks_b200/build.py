@@ -6,7 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmk.so")
-SOURCES = ["smk_boxes.cu", "smk_skewers.cu", "smk_spectra1d.cu", "smk_pk.cu", "smk_capi.cu"]
+SOURCES = ["smk_boxes.cu", "smk_skewers.cu", "smk_spectra1d.cu", "smk_pk.cu", "smk_qso.cu", "smk_capi.cu"]
+# smk_qso.cu restates float64 numpy arithmetic operation by operation: no fused multiply-add contraction
+FILE_FLAGS = {"smk_qso.cu": ["-fmad=false"]}
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -29,7 +31,8 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(CSRC, src[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = ([nvcc] + flags + FILE_FLAGS.get(src, []) + (["-Xptxas", "-v"] if verbose else [])
+               + ["-c", os.path.join(CSRC, src), "-o", obj])
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out = p.communicate()[0].decode()
@@ -46,7 +49,12 @@ def build_variant(tag, defines):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in FLAGS if not f.startswith("--use_fast_math")] + ["-D" + d for d in defines]
     out = os.path.join(HERE, "libsmk_%s.so" % tag)
-    subprocess.check_call([nvcc] + flags + ["-shared", "-o", out] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lcudart"])
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, "%s_%s.o" % (src[:-3], tag))
+        subprocess.check_call([nvcc] + flags + FILE_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj])
+        objs.append(obj)
+    subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-lcudart"])
     return out
 
 

@@ -79,3 +79,11 @@ def p1dmiss_tables():
 
 def nz_qso_desi():
     return _npz()["nz_qso_desi"]
+
+
+def qso_lognormal_coef():
+    """z, coef columns of etc/qso_lognormal_coef.txt (py/SaclayMocks/util.py:520-536)."""
+    etc = _etc_dir()
+    if etc and os.path.isfile(etc + "/qso_lognormal_coef.txt"):
+        return np.loadtxt(etc + "/qso_lognormal_coef.txt")[:, :2]
+    return _npz()["qso_lognormal_coef"]

@@ -68,6 +68,7 @@ def main():
     out["p1dmiss_pk"] = np.array(pk)
     nz = np.loadtxt(REF + "nz_qso_desi.dat")
     out["nz_qso_desi"] = nz
+    out["qso_lognormal_coef"] = np.loadtxt(REF + "qso_lognormal_coef.txt")[:, :2]     # z, coef (util.py:520-536)
     dst = os.path.join(os.path.dirname(__file__), "..", "..", "saclaymocks_b200", "data", "etc_tables.npz")
     np.savez_compressed(dst, **out)
     print("wrote", os.path.abspath(dst), os.path.getsize(dst), "bytes")

@@ -195,9 +195,51 @@ def pipeline(tag, NX, NY, NZ, dcell, nslice, nq, half_angle, seed=42, keep_full=
     shutil.rmtree(tmp)
 
 
+def qso_case(tag, NX, NY, NZ, dcell, nslice, dra, ddec, seed=42, zfix=None):
+    """make_boxes.py -> draw_qso.py (one run per slice, -desi False: the DESI footprint map is a missing blob)
+    on a small box; stores the six input boxes of draw_qso and every column of the QSO-<i>-<nslice>.fits tables."""
+    from saclaymocks_b200 import fitsio_lite as fitsio
+    tmp = tempfile.mkdtemp(prefix="smk_refqso_" + tag)
+    d = {k: os.path.join(tmp, k) for k in ("pk", "boxes", "qso")}
+    for v in d.values():
+        os.makedirs(v)
+    ra0, dec0 = 190.0, 0.0
+    dims = ["-NX", NX, "-NY", NY, "-NZ", NZ]
+    run("interpolate_pk.py", dims + ["-pixel", dcell, "-i", 0, "-N", 1, "-outDir", d["pk"]])
+    run("merge_pk.py", dims + ["-inDir", d["pk"], "-outDir", d["pk"], "-N", 1])
+    run("make_boxes.py", dims + ["-pixel", dcell, "-nHDU", nslice, "-ncpu", 2, "-PkDir", d["pk"], "-seed", seed,
+                                 "-rsd", "True", "-outDir", d["boxes"]])
+    out = {"NX": NX, "NY": NY, "NZ": NZ, "dcell": dcell, "nslice": nslice, "seed": seed, "ra0": ra0, "dec0": dec0,
+           "dra": dra, "ddec": ddec, "chunk": 1, "zmin": 1.8, "zmax": 3.6, "zfix": -1.0 if zfix is None else zfix}
+    for name in ("boxln_1", "boxln_2", "boxln_3", "vx", "vy", "vz"):
+        out["box_" + name] = np.concatenate([fitsio.read(d["boxes"] + "/%s-%d.fits" % (name, i)) for i in range(nslice)])
+    for i in range(nslice):
+        a = ["-indir", d["boxes"], "-outpath", d["qso"], "-i", i, "-Nslice", nslice, "-chunk", 1, "-ra0", ra0,
+             "-dec0", dec0, "-dra", dra, "-ddec", ddec, "-zmin", 1.8, "-zmax", 3.6, "-desi", "False", "-seed", seed,
+             "-rsd", "True"]
+        if zfix is not None:
+            a += ["-zfix", zfix]
+        run("draw_qso.py", a)
+        f = fitsio.FITS(d["qso"] + "/QSO-%d-%d.fits" % (i, nslice))
+        t = f[1].read()
+        hd = f[1].read_header()
+        out["qso%d_seed" % i] = hd["seed"]
+        for c in ("Z_QSO_NO_RSD", "Z_QSO_RSD", "RA", "DEC", "HDU", "THING_ID", "PLATE", "MJD", "FIBERID", "PMF",
+                  "XX", "YY", "ZZ"):
+            out["qso%d_%s" % (i, c)] = t[c]
+        print("slice", i, "nqso", len(t))
+    dst = os.path.join(HERE, "ref_%s.npz" % tag)
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KiB")
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     install_shims()
+    if which in ("qso", "all"):
+        # 32 x 32 x 192 cells of 17.52 Mpc/h (LZ = 3364 Mpc/h like the nominal box), 2 slices
+        qso_case("qso", 32, 32, 192, 17.52, 2, dra=30.0, ddec=30.0)   # wide cut: ~1e3 quasars per slice
     if which in ("small", "all"):
         # 16 x 16 x 96 cells of 35.04 Mpc/h (LZ = 3364 Mpc/h like the nominal box), 4 x-slabs so that
         # some sightlines cross a slab boundary and exercise the piece merge (merge_spectra.py:282-300)

@@ -33,6 +33,23 @@ def test_python_binding_matches_header():
     assert ctypes.sizeof(_lib.Geom) == 3 * 4 + 4 + 4 * 8 + 4 + 4 + 8     # smk_geom with C padding
 
 
+def test_qso_params_layout_matches_the_header(tmp_path):
+    """struct smk_qso_params: the ctypes mirror has the size and field offsets gcc gives the C declaration."""
+    import subprocess
+    from saclaymocks_b200.qso import QsoParams
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu",'
+                   'sizeof(smk_qso_params),offsetof(smk_qso_params,x_axis),offsetof(smk_qso_params,sigma_p),'
+                   'offsetof(smk_qso_params,u1),offsetof(smk_qso_params,seed));return 0;}\n'
+                   % os.path.join(os.path.abspath(ROOT), "include", "smk.h"))
+    exe = str(tmp_path / "sz")
+    subprocess.check_call(["gcc", str(src), "-o", exe])
+    got = [int(v) for v in subprocess.check_output([exe]).split()]
+    want = [ctypes.sizeof(QsoParams), QsoParams.x_axis.offset, QsoParams.sigma_p.offset, QsoParams.u1.offset,
+            QsoParams.seed.offset]
+    assert got == want
+
+
 def test_product_refuses_to_run_without_cuda():
     import pytest
     import torch
