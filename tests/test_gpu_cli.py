@@ -84,3 +84,38 @@ def test_cli_chain_matches_reference_files(tmp_path, golden_small):
         assert np.max(np.abs(f["FLUX"].read() - g["merged_zfix_FLUX"][rows])) < 1e-5
         assert np.max(np.abs(f["DELTA_S"].read() - g["merged_zfix_DELTA_S"][rows])) < 2e-5
         assert np.max(np.abs(f["DELTA_L"].read() - g["merged_zfix_DELTA_L"][rows])) < 1e-5
+
+
+def test_draw_qso_cli_matches_reference_files(tmp_path):
+    """bin/draw_qso.py with the reference's CLI on the boxes the reference's make_boxes.py wrote: same quasars as the
+    unmodified reference draw_qso.py (tests/golden/ref_qso.npz), same table layout."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from saclaymocks_b200 import fitsio_lite as fitsio
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_qso.npz")))
+    NX, NY, NZ, dcell, ns = int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"]), int(g["nslice"])
+    boxes, out = str(tmp_path / "boxes"), str(tmp_path / "qso")
+    os.makedirs(boxes), os.makedirs(out)
+    for name in ("boxln_1", "boxln_2", "boxln_3", "vx", "vy", "vz"):
+        for i in range(ns):
+            f = fitsio.FITS(boxes + "/%s-%d.fits" % (name, i), "rw", clobber=True)
+            f.write(g["box_" + name][i * NX // ns:(i + 1) * NX // ns],
+                    header={"DX": dcell, "DY": dcell, "DZ": dcell, "NX": NX, "NY": NY, "NZ": NZ})
+            f.close()
+    for i in range(ns):
+        log = run("draw_qso.py", "-indir", boxes, "-outpath", out, "-i", i, "-Nslice", ns, "-chunk", int(g["chunk"]), "-ra0",
+                  float(g["ra0"]), "-dec0", float(g["dec0"]), "-dra", float(g["dra"]), "-ddec", float(g["ddec"]), "-zmin",
+                  1.8, "-zmax", 3.6, "-desi", "False", "-seed", int(g["seed"]), "-rsd", "True")
+        f = fitsio.FITS(out + "/QSO-%d-%d.fits" % (i, ns))
+        t, hd = f[1].read(), f[1].read_header()
+        assert hd["seed"] == int(g["seed"]) + i and hd["ra0"] == float(g["ra0"]) and hd["dec0"] == float(g["dec0"])
+        assert "%d QSOs drawn" % len(g["qso%d_RA" % i]) in log
+        for c in ("HDU", "THING_ID", "PLATE", "MJD", "FIBERID", "PMF", "XX"):
+            assert np.array_equal(t[c], g["qso%d_%s" % (i, c)]), (i, c)
+        for c in ("Z_QSO_NO_RSD", "Z_QSO_RSD", "RA", "DEC", "YY", "ZZ"):
+            assert t[c].dtype == g["qso%d_%s" % (i, c)].dtype
+            assert np.allclose(t[c], g["qso%d_%s" % (i, c)], rtol=3e-7, atol=0), (i, c)
+    assert run.__name__ == "run"
+    r = subprocess.run([sys.executable, os.path.join(BIN, "draw_qso.py"), "-indir", boxes, "-outpath", out, "-i", "0",
+                        "-Nslice", str(ns), "-desi", "True"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not supported" in r.stdout          # fails loudly instead of silently skipping
