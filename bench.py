@@ -211,6 +211,8 @@ def run_gpu(args):
     ra, dec, z, ra0, dec0 = synthetic_qsos(nx, ny)
     pipe.set_catalogue(ra, dec, z, ra0, dec0)
     pipe.set_weights(W)
+    half = CHUNKS.get(nx, (190.0, 0.0, 6.4 * nx / 512.0))[2]
+    pipe.set_footprint(ra0, dec0, half, half * ny / nx)
     cells = nx * ny * NZ
 
     def barrier():
@@ -247,6 +249,16 @@ def run_gpu(args):
     t_tot, t_box, t_skw = (float(v) for v in t.cpu())
     npx = pipe.forest_pixels_total()
 
+    # ---- quasar drawing on the resident boxes (reported beside the step, not part of `value`)
+    pipe.draw_qso(seed=1)
+    barrier()
+    tq = time.time()
+    nq_drawn = 0
+    for i in range(max(1, min(args.steps, 3))):
+        nq_drawn = len(pipe.draw_qso(seed=2 + i)["RA"])
+    barrier()
+    t_qso = 1e3 * (time.time() - tq) / max(1, min(args.steps, 3))
+
     # ---- end-to-end arm: pinned host weights in, all boxes + all spectra rows back to host, every step
     e2e = None
     if world == 1 and not args.no_e2e:
@@ -262,6 +274,18 @@ def run_gpu(args):
         e2e = {"value": cells / dt, "unit": "cells/s", "h2d_bytes_per_step": host["h2d_bytes"],
                "d2h_bytes_per_step": host["d2h_bytes"], "ms_per_step": 1e3 * dt, "steps": n_e2e,
                "skewer_pixels_per_s": npx / dt}
+        pipe.step_e2e_resident(host, seed=7)
+        barrier()
+        t0 = time.time()
+        for i in range(n_e2e):
+            pipe.step_e2e_resident(host, seed=8 + i)
+        barrier()
+        dtr = (time.time() - t0) / n_e2e
+        e2e["resident"] = {"value": cells / dtr, "unit": "cells/s", "ms_per_step": 1e3 * dtr,
+                           "h2d_bytes_per_step": host["h2d_bytes"],
+                           "d2h_bytes_per_step": 4 * pipe.out[0].numel() * 4 + 64 * nq_drawn,
+                           "what": "same chunk with the boxes kept in HBM: P(k) splines + sightlines in, quasars drawn on "
+                                   "the resident boxes (smk_draw_qso), quasar table + spectra rows out"}
         del host
 
     # ---- roofline of the dominant kernel (slowest FFT pass), algorithmic bytes per launch
@@ -308,6 +332,7 @@ def run_gpu(args):
                            "parallelism": "x-slabs over %d GPU(s), all-to-all transposes" % world},
                 "grf_cells_per_s_boxes": cells / (t_box * 1e-3), "box_cells_per_s": 13 * cells / (t_box * 1e-3),
                 "skewer_pixels_per_s": npx / (t_skw * 1e-3), "t_boxes_ms": t_box, "t_skewers_ms": t_skw,
+                "t_draw_qso_ms": t_qso, "nqso_drawn_rank0": int(nq_drawn),
                 "wall_s": wall, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": pipe.launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))

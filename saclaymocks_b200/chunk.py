@@ -52,6 +52,8 @@ class ChunkPipeline(object):
                 self._connect_exchange()
         self.W = None
         self.cat = None
+        self.footprint = None
+        self._qso_setup = None
         # kernels per step: 3 forward passes + 13 x 3 inverse passes + gather + small-scale + FGPA
         self.launches_per_step = 3 + 13 * 3 + 3
 
@@ -261,6 +263,31 @@ class ChunkPipeline(object):
         self.step_boxes(seed)
         self.step_skewers(seed)
 
+    # ------------------------------------------------------------------ quasars (draw_qso.py on the resident boxes)
+    def set_footprint(self, ra0, dec0, dra, ddec, zmin=1.8, zmax=3.6, chunk=1):
+        """Window of the chunk (submit_mocks.py chunk_parameters) used by draw_qso."""
+        self.footprint = dict(ra0=ra0, dec0=dec0, dra=dra, ddec=ddec, zmin=zmin, zmax=zmax, chunk=chunk)
+        self._qso_setup = None
+
+    def draw_qso(self, seed=0, uniforms=None):
+        """Quasars of this rank's slab from the resident lognormal and velocity boxes (smk_draw_qso; the slab plays
+        the role of the reference's slice `-i rank -Nslice nranks`).  sigma of the lognormal boxes comes from the sums
+        the c2r pass accumulated (no extra pass).  Philox draws unless `uniforms` (legacy NumPy stream) is given."""
+        from . import qso
+        fp, bs = self.footprint, self.bs
+        n = float(bs.nxl) * bs.NY * bs.NZ
+        st3 = self.stats[[_lib.PRODUCT_ID[k] for k in ("boxln_1", "boxln_2", "boxln_3")]].cpu().numpy()
+        sigma = tuple(float(np.float32(np.sqrt(max(s2 / n - (s1 / n) ** 2, 0.0)))) for s1, s2 in st3)
+        if self._qso_setup is None or self._qso_setup.sigma_p != sigma:
+            self._qso_setup = qso.QsoSetup(bs.nxl, bs.NY, bs.NZ, bs.NX, bs.dcell, self.rank, self.nranks, fp["ra0"],
+                                           fp["dec0"], fp["dra"], fp["ddec"], fp["zmin"], fp["zmax"], sigma,
+                                           dmax=self.dmax)
+        if getattr(self, "_qso_drawer", None) is None:
+            self._qso_drawer = qso.QsoDrawer(bs)
+        return self._qso_drawer.draw(self._qso_setup, [self.interior("boxln_%d" % k) for k in (1, 2, 3)],
+                                     [self.interior(k) for k in ("vx", "vy", "vz")] if self.rsd else None,
+                                     ix0=self.rank * bs.nxl, uniforms=uniforms, seed=seed, chunk=fp["chunk"])
+
     # ------------------------------------------------------------------ end-to-end through host buffers (1 GPU)
     def make_host_buffers(self, W_dev):
         bs = self.bs
@@ -279,6 +306,36 @@ class ChunkPipeline(object):
                              + self.cat["nfor"].nbytes)
         host["d2h_bytes"] = len(PRODUCTS) * bs.NX * bs.NY * bs.NZ * 4 + 4 * self.out[0].numel() * 4
         return host
+
+    def step_e2e_resident(self, host, seed=0):
+        """The chunk as one pipeline: host inputs in (P(k) splines, sightline catalogue), boxes stay in HBM, quasars are
+        drawn on the resident boxes (smk_draw_qso, Philox draws) and only the quasar table and the spectra rows go back
+        to the host -- no box ever crosses PCIe.  (The skewers use the catalogue given to set_catalogue so that the
+        workload is the one `value` is quoted on.)"""
+        assert self.nranks == 1 and self.footprint is not None
+        main = torch.cuda.current_stream(self.device)
+        cs = host["copy_stream"]
+        self.stats.zero_()
+        for k, (br_h, co_h, br_d, co_d) in host["pp"].items():
+            br_d.copy_(br_h, non_blocking=True)
+            co_d.copy_(co_h, non_blocking=True)
+            _lib.check(self.bs.lib.smk_pk_weights(self.bs.h, _ptr(br_d), _ptr(co_d), int(co_h.shape[1]),
+                                                  _ptr(self.W[k])))
+        c = self.cat
+        c["xyzr_d"].copy_(torch.from_numpy(c["xyzr"]), non_blocking=True)
+        c["nfor_d"].copy_(torch.from_numpy(c["nfor"]), non_blocking=True)
+        self.step_boxes(seed)
+        cat = self.draw_qso(seed)                 # synchronises (the table comes back to the host)
+        self.step_skewers(seed)
+        e = torch.cuda.Event()
+        e.record(main)
+        cs.wait_event(e)
+        with torch.cuda.stream(cs):
+            for h, d in zip(host["spec"], self.out):
+                h.copy_(d, non_blocking=True)
+        cs.synchronize()
+        main.synchronize()
+        return cat
 
     def step_e2e(self, host, seed=0):
         """Host inputs in (P(k) splines and the quasar catalogue, pinned), every box and every spectrum row out to

@@ -32,8 +32,9 @@ __device__ __forceinline__ double interp1d(const double* __restrict__ x, const d
 }
 
 __device__ __forceinline__ double bias_qso(double z) { return 3.7 * pow((1 + z) / (1 + 2.33), 1.7); }      // util.py:513
-__device__ __forceinline__ double a_of_z(double z, double zb, double bias_zb) {                               // util.py:517
-  return bias_qso(z) * (1 + zb) / (bias_zb * (1 + z));
+// util.py:517 with bias_qso(z) evaluated once per redshift (the reference evaluates the same expression per call)
+__device__ __forceinline__ double a_of_z(double z, double bias_z, double zb, double bias_zb) {
+  return bias_z * (1 + zb) / (bias_zb * (1 + z));
 }
 
 __device__ __forceinline__ double diffmod(double a, double b, double c) {       // util.py:116-120 (python %: sign of c)
@@ -62,9 +63,10 @@ __global__ void __launch_bounds__(256) draw_qso_kernel(const smk_qso_params p, i
     // ---- ptot (draw_qso.py:197-199, 237-249)
     const double z_box = interp1d(p.chi, p.zt, p.ntab, sqrt((xa * xa + ya * ya) + za * za) / p.h);
     const float e1 = expf(p.boxln[0][idx]), e2 = expf(p.boxln[1][idx]), e3 = expf(p.boxln[2][idx]);
-    const float p1 = (float)pow((double)e1, a_of_z(z_box, p.z1, bz1));
-    const float p2 = (float)pow((double)e2, a_of_z(z_box, p.z2, bz2));
-    const float p3 = (float)pow((double)e3, a_of_z(z_box, p.z3, bz3));
+    const double bzb = bias_qso(z_box);
+    const float p1 = (float)pow((double)e1, a_of_z(z_box, bzb, p.z1, bz1));
+    const float p2 = (float)pow((double)e2, a_of_z(z_box, bzb, p.z2, bz2));
+    const float p3 = (float)pow((double)e3, a_of_z(z_box, bzb, p.z3, bz3));
     const double p12 = (double)p1 * (p.z2 - z_box) / (p.z2 - p.z1) + (double)p2 * (z_box - p.z1) / (p.z2 - p.z1);
     const double p23 = (double)p2 * (p.z3 - z_box) / (p.z3 - p.z2) + (double)p3 * (z_box - p.z2) / (p.z3 - p.z2);
     const double ptot = interp1d(p.coef_z, p.coef_v, p.ncoef, z_box) * (p12 - p23) + p23;
@@ -99,8 +101,9 @@ __global__ void __launch_bounds__(256) draw_qso_kernel(const smk_qso_params p, i
     double density = p.dn_cell[izn];
     {
       const double c = interp1d(p.coef_z, p.coef_v, p.ncoef, z0c);
-      const double a1 = a_of_z(z0c, p.z1, bz1) * p.sigma_p[0], a2 = a_of_z(z0c, p.z2, bz2) * p.sigma_p[1],
-                   a3 = a_of_z(z0c, p.z3, bz3) * p.sigma_p[2];
+      const double b0 = bias_qso(z0c);
+      const double a1 = a_of_z(z0c, b0, p.z1, bz1) * p.sigma_p[0], a2 = a_of_z(z0c, b0, p.z2, bz2) * p.sigma_p[1],
+                   a3 = a_of_z(z0c, b0, p.z3, bz3) * p.sigma_p[2];
       const double g1 = exp(a1 * a1 / 2), g2 = exp(a2 * a2 / 2), g3 = exp(a3 * a3 / 2);
       density /= (c * (g1 * (p.z2 - z0c) / (p.z2 - p.z1) + g2 * (z0c - p.z1) / (p.z2 - p.z1)) +
                   (1 - c) * (g2 * (p.z3 - z0c) / (p.z3 - p.z2) + g3 * (z0c - p.z2) / (p.z3 - p.z2)));

@@ -162,27 +162,18 @@ class QsoDrawer(object):
     def _dev(self, a):
         return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
 
-    def draw(self, setup, boxln, velo=None, ix0=0, uniforms=None, seed=0, capacity=None, chunk=0, rs=None):
-        """boxln: three device float32 [NXs, NY, NZ] tensors (boxln_1..3 of this slab, NOT exponentiated);
-        velo: (vx, vy, vz) or None (rsd off).  Returns the QSO-<i>-<N>.fits columns as a dict of numpy arrays."""
-        st = setup
-        dev = self.device
-        for t in tuple(boxln) + tuple(velo or ()):
-            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
-            assert tuple(t.shape) == (st.NXs, st.NY, st.NZ), t.shape
+    def _prepared(self, st):
+        """Device copies of the set-up's tables and the scalar half of smk_qso_params (cached per set-up)."""
+        if getattr(st, "_prepared", None) is not None and st._prepared[2] == self.device:
+            return st._prepared[0], st._prepared[1]
         p = QsoParams()
-        p.nxs, p.ny, p.nz, p.ix0, p.nx_full = st.NXs, st.NY, st.NZ, int(ix0), st.NX_full
         keep = []
-        for k in range(3):
-            p.boxln[k] = boxln[k].data_ptr()
-            p.velo[k] = velo[k].data_ptr() if velo is not None else None
-        p.rsd = int(velo is not None)
 
         def put(name, arr):
             t = self._dev(arr)
             keep.append(t)
             setattr(p, name, t.data_ptr())
-            return t
+        p.nxs, p.ny, p.nz, p.nx_full = st.NXs, st.NY, st.NZ, st.NX_full
         put("x_axis", st.x_axis), put("y_axis", st.y_axis), put("z_axis", st.z_axis)
         p.dx = p.dy = p.dz = st.dcell
         put("chi", st.cosmo.chi), put("zt", st.cosmo.z)
@@ -201,12 +192,37 @@ class QsoDrawer(object):
         p.ra0, p.dec0, p.dra, p.ddec = st.ra0, st.dec0, st.dra, st.ddec
         r0, d0 = np.radians(st.ra0), np.radians(st.dec0)
         p.cr0, p.sr0, p.cd0, p.sd0 = float(np.cos(r0)), float(np.sin(r0)), float(np.cos(d0)), float(np.sin(d0))
+        st._prepared = (p, keep, self.device)
+        return p, keep
+
+    def draw(self, setup, boxln, velo=None, ix0=0, uniforms=None, seed=0, capacity=None, chunk=0, rs=None):
+        """boxln: three device float32 [NXs, NY, NZ] tensors (boxln_1..3 of this slab, NOT exponentiated);
+        velo: (vx, vy, vz) or None (rsd off).  Returns the QSO-<i>-<N>.fits columns as a dict of numpy arrays."""
+        st = setup
+        dev = self.device
+        for t in tuple(boxln) + tuple(velo or ()):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+            assert tuple(t.shape) == (st.NXs, st.NY, st.NZ), t.shape
+        p, keep = self._prepared(st)
+        p.ix0 = int(ix0)
+        for k in range(3):
+            p.boxln[k] = boxln[k].data_ptr()
+            p.velo[k] = velo[k].data_ptr() if velo is not None else None
+        p.rsd = int(velo is not None)
+        for name in ("u1", "u2", "ux", "uy", "uz"):
+            setattr(p, name, None)
+        keep = list(keep)
+
+        def put(name, arr):
+            t = self._dev(arr)
+            keep.append(t)
+            setattr(p, name, t.data_ptr())
         if uniforms is not None:
             for name, u in zip(("u1", "u2", "ux", "uy", "uz"), uniforms):
                 put(name, u)
         p.seed = int(seed) & (2 ** 64 - 1)
         if capacity is None:       # ~ norm * <ptot> of the cells pass cond1; a fraction of those survives
-            capacity = int(64 + 4e-3 * st.NXs * st.NY * st.NZ)
+            capacity = int(1024 + 1e-3 * st.NXs * st.NY * st.NZ)
         while True:
             counters = torch.zeros(2, dtype=torch.int32, device=dev)
             records = torch.empty((capacity, 8), dtype=torch.float64, device=dev)
