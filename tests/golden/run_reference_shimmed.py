@@ -234,9 +234,57 @@ def qso_case(tag, NX, NY, NZ, dcell, nslice, dra, ddec, seed=42, zfix=None):
     shutil.rmtree(tmp)
 
 
+def trans_case():
+    """make_transmissions.py on spectra_merged files rebuilt from ref_small.npz (FLUX rows of the -zfix run): stores,
+    per transmission file, the header keys, MOCKIDs (sorted: the reference concatenates in glob order) and HDU names."""
+    from saclaymocks_b200 import fitsio_lite as fitsio
+    from saclaymocks_b200.healpix import radec2pix
+    g = dict(np.load(os.path.join(HERE, "ref_small.npz")))
+    tmp = tempfile.mkdtemp(prefix="smk_reftrans")
+    ind, outd = tmp + "/in", tmp + "/out"
+    ids = g["merged_zfix_THING_ID"]
+    order = {t: i for i, t in enumerate(g["qso_THING_ID"])}
+    rows = np.array([order[t] for t in ids])
+    ra, dec, zn, zr, hdu = (g["qso_" + k][rows] for k in ("RA", "DEC", "Z_QSO_NO_RSD", "Z_QSO_RSD", "HDU"))
+    pix = radec2pix(16, ra, dec, nest=True)
+    os.makedirs(ind + "/chunk_1/spectra_merged")
+    for p in np.unique(pix):
+        os.makedirs(outd + "/{}/{}".format(p // 100, p), exist_ok=True)
+        for h in np.unique(hdu[pix == p]):
+            m = np.where((pix == p) & (hdu == h))[0]
+            f = fitsio.FITS(ind + "/chunk_1/spectra_merged/spectra_merged-{}-{}.fits.gz".format(p, h), "rw", clobber=True)
+            f.write([ra[m], dec[m], zn[m], zr[m], hdu[m], ids[m]], names=["RA", "DEC", "Z_noRSD", "Z", "HDU", "THING_ID"],
+                    extname="METADATA")
+            f.write(g["merged_zfix_LAMBDA"], extname="LAMBDA")
+            f.write(g["merged_zfix_FLUX"][m], extname="FLUX")
+            f.close()
+    run("make_transmissions.py", ["-inDir", ind, "-outDir", outd, "-job", 0, "-ncpu", 1, "-nside", 16, "-nest", "True"])
+    out = {}
+    for f in sorted(glob.glob(outd + "/*/*/transmission-*.fits.gz")):
+        key = os.path.basename(f).split(".")[0].replace("-", "_")
+        ff = fitsio.FITS(f)
+        hd = ff["METADATA"].read_header()
+        md = ff["METADATA"].read()
+        o = np.argsort(md["MOCKID"])
+        out[key + "_path"] = os.path.relpath(f, outd)
+        out[key + "_hdus"] = np.array([h.get_extname() for h in ff])
+        for k in ("HPXNSIDE", "HPXNEST", "OL", "OM", "OK", "H0", "HPXPIXEL", "NSIDE"):
+            out[key + "_hdr_" + k] = hd[k]
+        for c in ("RA", "DEC", "Z_noRSD", "Z", "MOCKID"):
+            out[key + "_" + c] = md[c][o]
+        out[key + "_WAVELENGTH"] = ff["WAVELENGTH"].read()
+        out[key + "_TRANSMISSION_sum"] = ff["TRANSMISSION"].read()[o].astype("f8").sum(axis=1)
+    dst = os.path.join(HERE, "ref_trans.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KiB", len(out))
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     install_shims()
+    if which in ("trans",):
+        trans_case()
     if which in ("qso", "all"):
         # 32 x 32 x 192 cells of 17.52 Mpc/h (LZ = 3364 Mpc/h like the nominal box), 2 slices
         qso_case("qso", 32, 32, 192, 17.52, 2, dra=30.0, ddec=30.0)   # wide cut: ~1e3 quasars per slice
