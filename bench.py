@@ -332,7 +332,8 @@ def run_gpu(args):
                            "parallelism": "x-slabs over %d GPU(s), all-to-all transposes" % world},
                 "grf_cells_per_s_boxes": cells / (t_box * 1e-3), "box_cells_per_s": 13 * cells / (t_box * 1e-3),
                 "skewer_pixels_per_s": npx / (t_skw * 1e-3), "t_boxes_ms": t_box, "t_skewers_ms": t_skw,
-                "t_draw_qso_ms": t_qso, "nqso_drawn_rank0": int(nq_drawn),
+                "t_draw_qso_ms": t_qso, "t_draw_qso_kernel_ms": pipe._qso_drawer.last_kernel_ms,
+                "nqso_drawn_rank0": int(nq_drawn),
                 "wall_s": wall, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": pipe.launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))

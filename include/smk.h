@@ -82,6 +82,13 @@ int smk_timing_collect(smk_ctx* ctx, double ms_sum[SMK_NPASSES], int count[SMK_N
  * wtable: device float [nx][ny/R][nz/2+1], directly usable as the `wtable` argument of smk_synth_c2r. */
 int smk_pk_weights(smk_ctx* ctx, const double* breaks, const double* coefs, int nint, float* wtable);
 
+/* ---- 3-D power spectrum estimator on the GPU (the estimator the statistical acceptance
+ * tests use, P(k) = <|delta_k|^2> V / N^2): bins |boxk|^2 of this rank's k-slab of a forward transform (smk_fft_r2c of a
+ * real box) into `nbins` equal bins of |k| in [kmin, kmax) (h/Mpc), weighting every mode with its Hermitian
+ * multiplicity.  sums: device double [3][nbins], ACCUMULATED (zero first; all-reduce over ranks): sum of mult*|boxk|^2,
+ * sum of mult, sum of mult*|k|. */
+int smk_pk_estimate(smk_ctx* ctx, const void* boxk, int nbins, double kmin, double kmax, double* sums);
+
 /* ---- white noise.  Replaces the np.random.normal plane loop of DrawGRF_boxk (make_boxes.py:46-48)
  * with Philox4x32-10 keyed by (seed, global cell index): identical for any slab decomposition. */
 int smk_noise_philox(smk_ctx* ctx, uint64_t seed, float* box_slab);

@@ -121,6 +121,28 @@ class BoxSynth(object):
                                           C.c_double(self.dgrowth0), _ptr(out), _ptr(stats)))
         return out, stats
 
+    def power_spectrum(self, box, nbins=30, kmin=0.05, kmax=None, group=None):
+        """P(k) of a real box (this rank's x-slab) on the GPU: forward r2c with the library's own FFT, then
+        smk_pk_estimate.  Returns (k_mean, P, n_modes) per bin with P = <|delta_k|^2> V / N^2 and n_modes the number of
+        independent complex modes (the mode-count error of a Gaussian field is P / sqrt(n_modes)).  Single rank, or
+        all ranks collectively with boxk exchanged by the caller's pipeline (use ChunkPipeline for multi-GPU)."""
+        assert self.nranks == 1, "multi-rank: run the forward transform through ChunkPipeline.forward"
+        boxk = self.empty_boxk()
+        _lib.check(self.lib.smk_fft_r2c(self.h, _ptr(box), C.c_uint64(0), _ptr(boxk)))
+        return self.power_spectrum_of_boxk(boxk, nbins, kmin, kmax)
+
+    def power_spectrum_of_boxk(self, boxk, nbins=30, kmin=0.05, kmax=None, group=None):
+        kmax = 0.9 * np.pi / self.dcell if kmax is None else kmax
+        sums = torch.zeros((3, nbins), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.smk_pk_estimate(self.h, _ptr(boxk), nbins, C.c_double(kmin), C.c_double(kmax), _ptr(sums)))
+        if self.nranks > 1:
+            torch.distributed.all_reduce(sums, group=group)
+        s = sums.cpu().numpy()
+        N = float(self.NX) * self.NY * self.NZ
+        vol = N * self.dcell ** 3
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return s[2] / s[1], s[0] / s[1] * vol / N ** 2, s[1] / 2.0
+
     def sigma(self, stats, ncells=None):
         """np.std(box) from the fused sums (make_boxes.py:92); raises like make_boxes.py:100-105 on a null box."""
         s1, s2 = (float(v) for v in stats.cpu())

@@ -281,7 +281,7 @@ class ChunkPipeline(object):
         if self._qso_setup is None or self._qso_setup.sigma_p != sigma:
             self._qso_setup = qso.QsoSetup(bs.nxl, bs.NY, bs.NZ, bs.NX, bs.dcell, self.rank, self.nranks, fp["ra0"],
                                            fp["dec0"], fp["dra"], fp["ddec"], fp["zmin"], fp["zmax"], sigma,
-                                           dmax=self.dmax)
+                                           dmax=self.dmax, rho_sum=qso.scaled_rho_sum(n))
         if getattr(self, "_qso_drawer", None) is None:
             self._qso_drawer = qso.QsoDrawer(bs)
         return self._qso_drawer.draw(self._qso_setup, [self.interior("boxln_%d" % k) for k in (1, 2, 3)],

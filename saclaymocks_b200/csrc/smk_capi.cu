@@ -292,6 +292,12 @@ int smk_pk_weights(smk_ctx* c, const double* breaks, const double* coefs, int ni
   return launch_pk_weights(p, c->stream);
 }
 
+int smk_pk_estimate(smk_ctx* c, const void* boxk, int nbins, double kmin, double kmax, double* sums) {
+  if (!boxk || !sums) { set_error("smk_pk_estimate: null argument"); return SMK_ERR_ARG; }
+  return launch_pk_estimate((const float2*)boxk, c->kx, c->ky, c->kz, c->nx, c->nyl, c->nzh, c->pitch, c->rank * c->nyl,
+                            c->nz, nbins, kmin, kmax, sums, c->stream);
+}
+
 int smk_timing_enable(smk_ctx* c, int on) {
   c->timing = on != 0;
   c->ev_used = 0;

@@ -88,6 +88,9 @@ struct PkParams {
 };
 int launch_pk_weights(const PkParams& p, cudaStream_t st);
 
+int launch_pk_estimate(const float2* boxk, const float* kx, const float* ky, const float* kz, int nx, int nyl, int nzh,
+                       int pitch, int y0, int nz, int nbins, double kmin, double kmax, double* out, cudaStream_t st);
+
 int prefetch_distance();
 bool strided_size_supported(int n);
 int strided_tile_width(int n);   // kz columns per tile of the strided pass of length n

@@ -32,6 +32,53 @@ __global__ void pk_weights_kernel(PkParams p) {
   }
 }
 
+// ---- 3-D power spectrum estimator: bins |boxk|^2 of this rank's k-slab in |k| with the
+// Hermitian multiplicity of the half-complex layout (planes kz = 0 and kz = Nyquist count once, the others twice).
+// Per bin: sum of mult * |boxk|^2, sum of mult, sum of mult * |k| (double).  Block-local histograms in shared memory,
+// one atomicAdd per bin and block at the end.
+struct PkEstParams {
+  const float2* boxk;
+  const float *kx, *ky, *kz;
+  int nx, nyl, nzh, pitch, y0, nz_even;
+  int nbins;
+  float kmin, inv_dk;
+  double* out;       // [3][nbins]
+};
+
+__global__ void __launch_bounds__(256) pk_estimate_kernel(PkEstParams p) {
+  extern __shared__ double sh[];                 // [3][nbins]
+  for (int i = threadIdx.x; i < 3 * p.nbins; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const size_t n = (size_t)p.nx * p.nyl * p.nzh;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int iz = (int)(idx % p.nzh);
+    const size_t t = idx / p.nzh;
+    const int iy = (int)(t % p.nyl), ix = (int)(t / p.nyl);
+    const float kx = __ldg(p.kx + ix), ky = __ldg(p.ky + p.y0 + iy), kz = __ldg(p.kz + iz);
+    const float k = sqrtf(kx * kx + ky * ky + kz * kz);
+    const int b = (int)floorf((k - p.kmin) * p.inv_dk);
+    if (b < 0 || b >= p.nbins) continue;
+    const float2 v = p.boxk[((size_t)ix * p.nyl + iy) * p.pitch + iz];
+    const double m = (iz == 0 || (p.nz_even && iz == p.nzh - 1)) ? 1.0 : 2.0;
+    atomicAdd(sh + b, m * ((double)v.x * v.x + (double)v.y * v.y));
+    atomicAdd(sh + p.nbins + b, m);
+    atomicAdd(sh + 2 * p.nbins + b, m * (double)k);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * p.nbins; i += blockDim.x)
+    if (sh[i] != 0.0) atomicAdd(p.out + i, sh[i]);
+}
+
+int launch_pk_estimate(const float2* boxk, const float* kx, const float* ky, const float* kz, int nx, int nyl, int nzh,
+                       int pitch, int y0, int nz, int nbins, double kmin, double kmax, double* out, cudaStream_t st) {
+  if (nbins < 1 || nbins > 2048 || !(kmax > kmin)) { set_error("smk_pk_estimate: need 1..2048 bins and kmax > kmin"); return SMK_ERR_ARG; }
+  PkEstParams p{boxk, kx, ky, kz, nx, nyl, nzh, pitch, y0, nz % 2 == 0, nbins, (float)kmin,
+                (float)(nbins / (kmax - kmin)), out};
+  pk_estimate_kernel<<<148 * 8, 256, 3 * nbins * sizeof(double), st>>>(p);
+  SMK_CUDA_OK(cudaGetLastError());
+  return SMK_OK;
+}
+
 int launch_pk_weights(const PkParams& p, cudaStream_t st) {
   pk_weights_kernel<<<148 * 16, 256, 0, st>>>(p);
   SMK_CUDA_OK(cudaGetLastError());

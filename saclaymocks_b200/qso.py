@@ -19,7 +19,8 @@ from . import tables
 
 N_QSO_EXP = 100.0         # constant.py:8
 QSO_NZ_ADHOC = 0.213      # constant.py:9
-RHO_SUM = 16452460        # constant.py:42
+RHO_SUM = 16452460        # constant.py:42: sum of ptot over one slice of the nominal box (2560 x 2560 x 1536 / 512)
+NOMINAL_SLICE_CELLS = 2560 * 2560 * 1536 // 512
 
 
 def bias_qso(z):
@@ -61,7 +62,10 @@ class QsoSetup(object):
     """Geometry, n(z) and normalisation of one slice (draw_qso.py:196-360).  sigma_p: std of the three lognormal
     boxes of this slice (draw_qso.py:191-193)."""
 
-    def __init__(self, NXs, NY, NZ, NX_full, dcell, i_slice, nslice, ra0, dec0, dra, ddec, zmin, zmax, sigma_p, dmax=3):
+    def __init__(self, NXs, NY, NZ, NX_full, dcell, i_slice, nslice, ra0, dec0, dra, ddec, zmin, zmax, sigma_p, dmax=3,
+                 rho_sum=RHO_SUM):
+        """rho_sum: the reference hard-codes the nominal slice's sum of ptot (constant.rho_sum, draw_qso.py:235,345);
+        a caller whose slab is not a nominal slice passes scaled_rho_sum(cells) to keep the quasar density."""
         h = constant.h
         cs = cosmo_mod.cosmo(constant.omega_M_0, Ok=constant.omega_k_0, H0=100 * h)
         self.cosmo = cs
@@ -109,7 +113,7 @@ class QsoSetup(object):
         m = (self.dz_interp > z_min) & (self.dz_interp < z_max)
         mean_rho = dn_cell[m] / self.cond1_correction(self.dz_interp[m])
         self.density_max = float(np.max(mean_rho))
-        norm = nQSOexp / RHO_SUM
+        norm = nQSOexp / rho_sum
         norm *= self.density_max / np.mean(mean_rho)
         norm /= volFrac
         if z_max > 2.1:
@@ -131,6 +135,11 @@ class QsoSetup(object):
         g = lambda zb, s: np.exp((qso_a_of_z(z, zb) * s) ** 2 / 2)      # noqa: E731
         return (c * (g(z1, s1) * (z2 - z) / (z2 - z1) + g(z2, s2) * (z - z1) / (z2 - z1))
                 + (1 - c) * (g(z2, s2) * (z3 - z) / (z3 - z2) + g(z3, s3) * (z - z2) / (z3 - z2)))
+
+
+def scaled_rho_sum(ncells):
+    """constant.rho_sum rescaled from the nominal slice to a slab of `ncells` cells (<ptot> per cell unchanged)."""
+    return RHO_SUM * (float(ncells) / NOMINAL_SLICE_CELLS)
 
 
 def legacy_uniforms(seed, NXs, NY, NZ):
@@ -226,9 +235,13 @@ class QsoDrawer(object):
         while True:
             counters = torch.zeros(2, dtype=torch.int32, device=dev)
             records = torch.empty((capacity, 8), dtype=torch.float64, device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.bs.stream)
             _lib.check(self.lib.smk_draw_qso(self.bs.h, C.byref(p), C.c_void_p(counters.data_ptr()),
                                              C.c_void_p(records.data_ptr()), capacity))
+            e1.record(self.bs.stream)
             n, nn = (int(v) for v in counters.cpu())
+            self.last_kernel_ms = e0.elapsed_time(e1)
             if n <= capacity:
                 break
             capacity = n + 64          # the record buffer was too small: run again with room for every quasar

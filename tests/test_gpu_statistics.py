@@ -88,3 +88,34 @@ def test_small_scale_p1d_matches_input(cuda):
     ds2 = fg.small_scales(nf[:4], seed=99, qso_ids=np.arange(4))
     assert torch.equal(ds2, ds[:4])
     assert float((ds[0] * ds[1]).mean().abs()) < 0.2 * float((ds[0] ** 2).mean())
+
+
+def test_gpu_pk_estimator_matches_independent_estimator(cuda):
+    """smk_pk_estimate (own r2c + binning kernel) against the torch.fft / numpy estimator above, bin by bin, and
+    against the input P0 within the mode-count error."""
+    from saclaymocks_b200 import pk
+    from saclaymocks_b200.boxes import BoxSynth
+    NX, NY, NZ, dcell = 128, 64, 256, 2.19
+    bs = BoxSynth(NX, NY, NZ, dcell, device=cuda)
+    W = pk.weight_tables(NX, NY, NZ, dcell)
+    boxk = bs.draw_grf_boxk(seed=7)
+    box, _ = bs.synth(boxk, "box", wtable=bs.upload_weights(W["P0"]))
+    nb, kmin, kmax = 24, 0.05, 0.9 * np.pi / dcell
+    kmean, P, nmodes = bs.power_spectrum(box, nbins=nb, kmin=kmin, kmax=kmax)
+    dk = torch.fft.rfftn(box.double())
+    N = NX * NY * NZ
+    p3d = (dk.abs() ** 2 * (N * dcell ** 3) / N ** 2).cpu().numpy().ravel()
+    k = pk.k_norm(NX, NY, NZ, dcell).astype(np.float32).ravel()
+    mult = np.full(NZ // 2 + 1, 2.0)
+    mult[0] = mult[-1] = 1.0
+    mult = np.broadcast_to(mult, (NX, NY, NZ // 2 + 1)).ravel()
+    b = np.floor((k - np.float32(kmin)) * np.float32(nb / (kmax - kmin))).astype(int)
+    for i in range(nb):
+        m = b == i
+        assert abs(nmodes[i] - mult[m].sum() / 2) <= 2              # float32 bin edges: at most a couple of modes move
+        ref = (p3d[m] * mult[m]).sum() / mult[m].sum()
+        assert abs(P[i] / ref - 1) < 2e-3, (i, P[i], ref)
+        assert abs(kmean[i] - (k[m] * mult[m]).sum() / mult[m].sum()) < 1e-4
+        truth = (np.maximum(pk.spline("P0")(k[m].astype(np.float64)), 0) * mult[m]).sum() / mult[m].sum()
+        assert abs(P[i] / truth - 1) < 5.5 / np.sqrt(nmodes[i]), i
+    bs.close()
