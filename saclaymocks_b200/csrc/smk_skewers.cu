@@ -34,7 +34,7 @@ struct SkewerParams {
   float* delta_l;
   float* eta_par;
   float* vpar;
-  int pf;                  // tuning: 0 none, 1 = L2 prefetch of the next x slab of the window, 2 = L1 prefetch of the next row, 3 = both
+  int pf;                  // tuning bits: 1 = L2 prefetch of the next x slab of the window, 2 = L1 prefetch of the next row, 4 = L1 prefetch of the next x slab
 };
 
 // Blackwell packed FP32: one FFMA2 / FMUL2 issues two fused multiply-adds (fma.rn.f32x2, sm_100+)
@@ -246,6 +246,15 @@ __device__ __forceinline__ void gather_multi2(const SkewerParams& p, const float
       for (int b = 0; b < nyu; ++b)
 #pragma unroll
         for (int f = 0; f < NF; ++f) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp[f] + nrow + (size_t)b * p.nz));
+    }
+    if (INTERIOR && (p.pf & 4) && a + 1 < nxu) {       // same, into L1 (both sectors the window can straddle)
+      const size_t nrow = (size_t)(la + 1) * plane + (unsigned)(by - DMAX) * (unsigned)p.nz + z0;
+      for (int b = 0; b < nyu; ++b)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow + (size_t)b * p.nz));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow + (size_t)b * p.nz + WU - 1));
+        }
     }
     float wxa[P];
 #pragma unroll

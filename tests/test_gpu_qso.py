@@ -92,3 +92,31 @@ def test_gpu_philox_selection_rate(cuda):
     assert not np.array_equal(c1["cells"], c3["cells"])
     n1, n3 = len(c1["RA"]), len(c3["RA"])
     assert abs(n1 - n_np) < 6 * np.sqrt(n_np) + 5 and abs(n3 - n_np) < 6 * np.sqrt(n_np) + 5
+
+
+def test_gpu_empty_selection_and_record_overflow(cuda):
+    """No quasar in the redshift window -> empty, well-formed table; a record buffer that is too small is detected
+    through counters[0] and the call repeated (same catalogue as with a large buffer)."""
+    from saclaymocks_b200 import qso
+    from saclaymocks_b200.boxes import BoxSynth
+    rng = np.random.default_rng(8)
+    NXs, NY, NZ, dcell = 16, 32, 384, 8.76
+    boxes = {k: (0.9 * rng.standard_normal((NXs, NY, NZ))).astype(np.float32) for k in ("boxln_1", "boxln_2", "boxln_3")}
+    boxes.update({k: (300 * rng.standard_normal((NXs, NY, NZ))).astype(np.float32) for k in ("vx", "vy", "vz")})
+    a = dict(NX_full=32, dcell=dcell, i_slice=0, nslice=2, chunk=1, ra0=190.0, dec0=5.0, dra=1e-7, ddec=1e-7, zmin=1.8,
+             zmax=3.6, seed=3)                                   # an angular window no cell centre falls into
+    cat = run_gpu(cuda, boxes, a, 0, philox_seed=1)
+    assert len(cat["RA"]) == 0 and cat["PMF"].dtype == np.dtype("S21") and cat["cells"].shape == (0, 3)
+    assert cat["nn_cond1"] > 0                                   # cells did pass cond1; cond3 removed them all
+    a["dra"] = a["ddec"] = 30.0
+    bs = BoxSynth(16, 16, 24, 2.19, device=cuda)
+    dev = {k: torch.as_tensor(v, device=cuda) for k, v in boxes.items()}
+    sig = tuple(float(np.float32(qso.box_sigma(dev[k]))) for k in ("boxln_1", "boxln_2", "boxln_3"))
+    st = qso.QsoSetup(NXs, NY, NZ, a["NX_full"], dcell, 0, 2, a["ra0"], a["dec0"], a["dra"], a["ddec"], 1.8, 3.6, sig,
+                      rho_sum=qso.scaled_rho_sum(NXs * NY * NZ) / 50)          # ~50x the nominal density
+    d = qso.QsoDrawer(bs)
+    args_ = ([dev["boxln_1"], dev["boxln_2"], dev["boxln_3"]], [dev["vx"], dev["vy"], dev["vz"]])
+    big = d.draw(st, *args_, seed=5)
+    small = d.draw(st, *args_, seed=5, capacity=3)
+    assert len(big["RA"]) > 10 and np.array_equal(big["f64"], small["f64"])
+    bs.close()
