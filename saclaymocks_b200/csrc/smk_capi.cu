@@ -42,6 +42,8 @@ struct smk_ctx {
   float2* yz_scratch = nullptr;
   cudaStream_t yz_stream[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t yz_fork = nullptr, yz_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* scratch = nullptr;      // small persistent scratch for kernels of other translation units (smk_ctx_scratch)
+  size_t scratch_bytes = 0;
   // optional per-pass CUDA-event timing (smk_timing_*): events are recorded around every pass kernel
   bool timing = false;
   std::vector<cudaEvent_t> ev;       // pool
@@ -255,7 +257,7 @@ int smk_ctx_destroy(smk_ctx* c) {
   if (!c) return SMK_OK;
   cudaFree(c->tw_x); cudaFree(c->tw_y); cudaFree(c->tw_z);
   cudaFree(c->kx); cudaFree(c->ky); cudaFree(c->kz);
-  cudaFree(c->work); cudaFree(c->stats); cudaFree(c->yz_scratch);
+  cudaFree(c->work); cudaFree(c->stats); cudaFree(c->yz_scratch); cudaFree(c->scratch);
   if (c->yz_fork) cudaEventDestroy(c->yz_fork);
   for (int s = 0; s < 4; ++s) {
     if (c->yz_join[s]) cudaEventDestroy(c->yz_join[s]);
@@ -595,3 +597,20 @@ int smk_make_boxes_host(smk_ctx* c, const float* noise_host, uint64_t seed, cons
 }  // extern "C"
 
 cudaStream_t smk_ctx_stream(const smk_ctx* ctx) { return ctx ? ctx->stream : (cudaStream_t)0; }
+
+void* smk_ctx_scratch(smk_ctx* c, size_t bytes) {
+  if (c->scratch_bytes >= bytes) return c->scratch;
+  if (c->scratch) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->scratch);
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
+  }
+  if (cudaMalloc(&c->scratch, bytes) != cudaSuccess) {
+    smk::set_error("smk_ctx_scratch: cudaMalloc failed");
+    c->scratch = nullptr;
+    return nullptr;
+  }
+  c->scratch_bytes = bytes;
+  return c->scratch;
+}

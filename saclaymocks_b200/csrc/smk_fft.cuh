@@ -13,18 +13,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define SMK_HD __host__ __device__ __forceinline__
+
 namespace smk {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+SMK_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+SMK_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+SMK_HD float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+SMK_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+SMK_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 // multiply by -i (forward) or +i (inverse)
 template <bool INV>
-__device__ __forceinline__ float2 mul_mi(float2 a) {
+SMK_HD float2 mul_mi(float2 a) {
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
 
@@ -49,7 +51,7 @@ struct Butterfly;
 
 template <bool INV>
 struct Butterfly<2, INV> {
-  static __device__ __forceinline__ void run(float2 (&v)[2]) {
+  static SMK_HD void run(float2 (&v)[2]) {
     float2 a = v[0], b = v[1];
     v[0] = cadd(a, b);
     v[1] = csub(a, b);
@@ -58,7 +60,7 @@ struct Butterfly<2, INV> {
 
 template <bool INV>
 struct Butterfly<3, INV> {
-  static __device__ __forceinline__ void run(float2 (&v)[3]) {
+  static SMK_HD void run(float2 (&v)[3]) {
     const float S3 = 0.86602540378443864676f;
     float2 s = cadd(v[1], v[2]), d = csub(v[1], v[2]);
     float2 m = make_float2(v[0].x - 0.5f * s.x, v[0].y - 0.5f * s.y);
@@ -71,7 +73,7 @@ struct Butterfly<3, INV> {
 
 template <bool INV>
 struct Butterfly<4, INV> {
-  static __device__ __forceinline__ void run(float2 (&v)[4]) {
+  static SMK_HD void run(float2 (&v)[4]) {
     float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
     float2 t2 = cadd(v[1], v[3]), t3 = mul_mi<INV>(csub(v[1], v[3]));
     v[0] = cadd(t0, t2);
@@ -83,7 +85,7 @@ struct Butterfly<4, INV> {
 
 template <bool INV>
 struct Butterfly<5, INV> {
-  static __device__ __forceinline__ void run(float2 (&v)[5]) {
+  static SMK_HD void run(float2 (&v)[5]) {
     const float C1 = 0.30901699437494742410f, C2 = -0.80901699437494742410f;
     const float S1 = 0.95105651629515357212f, S2 = 0.58778525229247312917f;
     float2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
@@ -102,7 +104,7 @@ struct Butterfly<5, INV> {
 
 template <bool INV>
 struct Butterfly<8, INV> {
-  static __device__ __forceinline__ void run(float2 (&v)[8]) {
+  static SMK_HD void run(float2 (&v)[8]) {
     const float H = 0.70710678118654752440f;
     float2 e[4] = {v[0], v[2], v[4], v[6]};
     float2 o[4] = {v[1], v[3], v[5], v[7]};
@@ -128,10 +130,10 @@ struct Butterfly<8, INV> {
 template <bool INV>
 struct Butterfly<16, INV> {
   // 4 x 4 decomposition: y[q1 + 4 q2] = sum_b w4^(b q2) w16^(b q1) [ sum_a x[4a+b] w4^(a q1) ]
-  static __device__ __forceinline__ float2 tw16(float2 v, float c, float s) {   // v * (c - i s) fwd, (c + i s) inv
+  static SMK_HD float2 tw16(float2 v, float c, float s) {   // v * (c - i s) fwd, (c + i s) inv
     return INV ? make_float2(v.x * c - v.y * s, v.y * c + v.x * s) : make_float2(v.x * c + v.y * s, v.y * c - v.x * s);
   }
-  static __device__ __forceinline__ void run(float2 (&v)[16]) {
+  static SMK_HD void run(float2 (&v)[16]) {
     const float H = 0.70710678118654752440f, C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f;
     float2 u[4][4];
 #pragma unroll
@@ -157,6 +159,94 @@ struct Butterfly<16, INV> {
       Butterfly<4, INV>::run(g);
 #pragma unroll
       for (int q2 = 0; q2 < 4; ++q2) v[q1 + 4 * q2] = g[q2];
+    }
+  }
+};
+
+// v * w^e with w = exp(-2 pi i / L) (forward) or its conjugate (INV); c = cos(2 pi e / L), s = sin(2 pi e / L)
+template <bool INV>
+SMK_HD float2 twc(float2 v, float c, float s) {
+  return INV ? make_float2(v.x * c - v.y * s, v.y * c + v.x * s) : make_float2(v.x * c + v.y * s, v.y * c - v.x * s);
+}
+
+template <bool INV>
+struct Butterfly<24, INV> {
+  // 3 x 8 decomposition, x index t = 3a + b (a < 8, b < 3), output q = q1 + 8 q2 (q1 < 8, q2 < 3):
+  //   y[q1 + 8 q2] = sum_b w3^(b q2) w24^(b q1) [ sum_a x[3a+b] w8^(a q1) ]
+  static SMK_HD void run(float2 (&v)[24]) {
+    float2 u[3][8];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      float2 g[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) g[a] = v[3 * a + b];
+      Butterfly<8, INV>::run(g);
+#pragma unroll
+      for (int q1 = 0; q1 < 8; ++q1) u[b][q1] = g[q1];
+    }
+    // cos/sin(2 pi e / 24), e = 0..14
+    const float C[15] = {1.f, 0.96592582628906828675f, 0.86602540378443864676f, 0.70710678118654752440f, 0.5f,
+                         0.25881904510252076235f, 0.f, -0.25881904510252076235f, -0.5f, -0.70710678118654752440f,
+                         -0.86602540378443864676f, -0.96592582628906828675f, -1.f, -0.96592582628906828675f,
+                         -0.86602540378443864676f};
+    const float S[15] = {0.f, 0.25881904510252076235f, 0.5f, 0.70710678118654752440f, 0.86602540378443864676f,
+                         0.96592582628906828675f, 1.f, 0.96592582628906828675f, 0.86602540378443864676f,
+                         0.70710678118654752440f, 0.5f, 0.25881904510252076235f, 0.f, -0.25881904510252076235f, -0.5f};
+#pragma unroll
+    for (int q1 = 1; q1 < 8; ++q1) {
+      u[1][q1] = twc<INV>(u[1][q1], C[q1], S[q1]);
+      u[2][q1] = twc<INV>(u[2][q1], C[2 * q1], S[2 * q1]);
+    }
+#pragma unroll
+    for (int q1 = 0; q1 < 8; ++q1) {
+      float2 g[3] = {u[0][q1], u[1][q1], u[2][q1]};
+      Butterfly<3, INV>::run(g);
+#pragma unroll
+      for (int q2 = 0; q2 < 3; ++q2) v[q1 + 8 * q2] = g[q2];
+    }
+  }
+};
+
+template <bool INV>
+struct Butterfly<32, INV> {
+  // 4 x 8 decomposition, x index t = 4a + b (a < 8, b < 4), output q = q1 + 8 q2 (q1 < 8, q2 < 4):
+  //   y[q1 + 8 q2] = sum_b w4^(b q2) w32^(b q1) [ sum_a x[4a+b] w8^(a q1) ]
+  static SMK_HD void run(float2 (&v)[32]) {
+    float2 u[4][8];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      float2 g[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) g[a] = v[4 * a + b];
+      Butterfly<8, INV>::run(g);
+#pragma unroll
+      for (int q1 = 0; q1 < 8; ++q1) u[b][q1] = g[q1];
+    }
+    // cos/sin(2 pi e / 32), e = 0..21
+    const float C[22] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                         0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                         0.19509032201612826785f, 0.f, -0.19509032201612826785f, -0.38268343236508977173f,
+                         -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                         -0.92387953251128675613f, -0.98078528040323044913f, -1.f, -0.98078528040323044913f,
+                         -0.92387953251128675613f, -0.83146961230254523708f, -0.70710678118654752440f,
+                         -0.55557023301960222474f};
+    const float S[22] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                         0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                         0.98078528040323044913f, 1.f, 0.98078528040323044913f, 0.92387953251128675613f,
+                         0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                         0.38268343236508977173f, 0.19509032201612826785f, 0.f, -0.19509032201612826785f,
+                         -0.38268343236508977173f, -0.55557023301960222474f, -0.70710678118654752440f,
+                         -0.83146961230254523708f};
+#pragma unroll
+    for (int b = 1; b < 4; ++b)
+#pragma unroll
+      for (int q1 = 1; q1 < 8; ++q1) u[b][q1] = twc<INV>(u[b][q1], C[b * q1], S[b * q1]);
+#pragma unroll
+    for (int q1 = 0; q1 < 8; ++q1) {
+      float2 g[4] = {u[0][q1], u[1][q1], u[2][q1], u[3][q1]};
+      Butterfly<4, INV>::run(g);
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) v[q1 + 8 * q2] = g[q2];
     }
   }
 };

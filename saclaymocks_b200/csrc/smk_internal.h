@@ -100,3 +100,5 @@ bool z_size_supported(int nz);
 
 // stream of a context (defined in smk_capi.cu; smk_ctx is opaque to the other translation units)
 cudaStream_t smk_ctx_stream(const smk_ctx* ctx);
+// persistent device scratch of at least `bytes` owned by the context (grown on demand; nullptr + error set on failure)
+void* smk_ctx_scratch(smk_ctx* ctx, size_t bytes);

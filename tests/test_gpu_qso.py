@@ -120,3 +120,29 @@ def test_gpu_empty_selection_and_record_overflow(cuda):
     small = d.draw(st, *args_, seed=5, capacity=3)
     assert len(big["RA"]) > 10 and np.array_equal(big["f64"], small["f64"])
     bs.close()
+
+
+def test_gpu_fast_kernel_probability_matches_oracle_ptot(cuda):
+    """Production (Philox) kernel: its float32 / tabulated ptot gives the cond1 acceptance the oracle's float64 ptot
+    predicts -- sum over cells of min(norm * ptot, 1) -- within the Poisson error, at ~50x the nominal density."""
+    from oracle import draw_qso as odq
+    from saclaymocks_b200 import qso
+    from saclaymocks_b200.boxes import BoxSynth
+    rng = np.random.default_rng(9)
+    NXs, NY, NZ, dcell = 32, 64, 384, 8.76
+    boxes = {k: (0.9 * rng.standard_normal((NXs, NY, NZ))).astype(np.float32) for k in ("boxln_1", "boxln_2", "boxln_3")}
+    boxes.update({k: (300 * rng.standard_normal((NXs, NY, NZ))).astype(np.float32) for k in ("vx", "vy", "vz")})
+    sig = tuple(float(np.std(boxes[k])) for k in ("boxln_1", "boxln_2", "boxln_3"))
+    common = (NXs, NY, NZ, 64, dcell, 1, 2, 190.0, 5.0, 30.0, 30.0, 1.8, 3.6, sig)
+    st = qso.QsoSetup(*common, rho_sum=qso.scaled_rho_sum(NXs * NY * NZ) / 50)
+    ost = odq.Setup(*common)
+    expected = float(np.minimum(st.norm * odq.ptot_box(ost, boxes["boxln_1"], boxes["boxln_2"], boxes["boxln_3"]), 1).sum())
+    bs = BoxSynth(16, 16, 24, 2.19, device=cuda)
+    dev = {k: torch.as_tensor(v, device=cuda) for k, v in boxes.items()}
+    d = qso.QsoDrawer(bs)
+    nn = [d.draw(st, [dev["boxln_1"], dev["boxln_2"], dev["boxln_3"]], [dev["vx"], dev["vy"], dev["vz"]], ix0=NXs,
+                 seed=s)["nn_cond1"] for s in (1, 2, 3, 4)]
+    assert expected > 2e4
+    assert abs(np.mean(nn) - expected) < 5 * np.sqrt(expected / len(nn)), (nn, expected)
+    assert len(set(nn)) > 1                                                  # different seeds, different draws
+    bs.close()
