@@ -124,7 +124,7 @@ def test_gpu_empty_selection_and_record_overflow(cuda):
 
 def test_gpu_fast_kernel_probability_matches_oracle_ptot(cuda):
     """Production (Philox) kernel: its float32 / tabulated ptot gives the cond1 acceptance the oracle's float64 ptot
-    predicts -- sum over cells of min(norm * ptot, 1) -- within the Poisson error, at ~50x the nominal density."""
+    predicts -- sum over cells of min(norm * ptot, 1) -- within the binomial error, at ~50x the nominal density."""
     from oracle import draw_qso as odq
     from saclaymocks_b200 import qso
     from saclaymocks_b200.boxes import BoxSynth
@@ -136,7 +136,9 @@ def test_gpu_fast_kernel_probability_matches_oracle_ptot(cuda):
     common = (NXs, NY, NZ, 64, dcell, 1, 2, 190.0, 5.0, 30.0, 30.0, 1.8, 3.6, sig)
     st = qso.QsoSetup(*common, rho_sum=qso.scaled_rho_sum(NXs * NY * NZ) / 50)
     ost = odq.Setup(*common)
-    expected = float(np.minimum(st.norm * odq.ptot_box(ost, boxes["boxln_1"], boxes["boxln_2"], boxes["boxln_3"]), 1).sum())
+    # P(cond1) = clip(norm * ptot, 0, 1): the linear z interpolation extrapolates to negative weights outside
+    # [z_QSO_bias_1, z_QSO_bias_3], so ptot can be negative (never selected)
+    expected = float(np.clip(st.norm * odq.ptot_box(ost, boxes["boxln_1"], boxes["boxln_2"], boxes["boxln_3"]), 0, 1).sum())
     bs = BoxSynth(16, 16, 24, 2.19, device=cuda)
     dev = {k: torch.as_tensor(v, device=cuda) for k, v in boxes.items()}
     d = qso.QsoDrawer(bs)
