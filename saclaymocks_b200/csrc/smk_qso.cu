@@ -235,19 +235,28 @@ __global__ void __launch_bounds__(256, 3) draw_qso_fast_kernel(const smk_qso_par
                      (uint32_t)iz4, 0x51u};
     philox4x32_10(c, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
     const float gg1[4] = {g1.x, g1.y, g1.z, g1.w}, gg2[4] = {g2.x, g2.y, g2.z, g2.w}, gg3[4] = {g3.x, g3.y, g3.z, g3.w};
-    unsigned hit = 0;
+    // (w_k, a_k) at the first and last cell of the quad from the table, linear in between (R is linear in the cell
+    // index to 1e-3 Mpc/h over four cells, the tabulated functions to ~1e-5)
+    float wq[2][3], aq[2][3];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float za = (float)__ldg(p.z_axis + 4 * iz4 + j);
+    for (int e = 0; e < 2; ++e) {
+      const float za = (float)__ldg(p.z_axis + 4 * iz4 + 3 * e);
       const float tt = (sqrtf(fmaf(za, za, xy2)) - r_lo) * inv_dr;
       int i = (int)tt;
       i = i < 0 ? 0 : (i > SMK_QSO_LUT - 1 ? SMK_QSO_LUT - 1 : i);
       const float f = tt - (float)i;
       const float4 w0 = *reinterpret_cast<const float4*>(lut->e[i]), a0 = *reinterpret_cast<const float4*>(lut->e[i] + 4);
       const float4 w1 = *reinterpret_cast<const float4*>(lut->e[i + 1]), a1 = *reinterpret_cast<const float4*>(lut->e[i + 1] + 4);
-      const float pt = fmaf(fmaf(f, w1.x - w0.x, w0.x), __expf(fmaf(f, a1.x - a0.x, a0.x) * gg1[j]),
-                            fmaf(fmaf(f, w1.y - w0.y, w0.y), __expf(fmaf(f, a1.y - a0.y, a0.y) * gg2[j]),
-                                 fmaf(f, w1.z - w0.z, w0.z) * __expf(fmaf(f, a1.z - a0.z, a0.z) * gg3[j])));
+      wq[e][0] = fmaf(f, w1.x - w0.x, w0.x); wq[e][1] = fmaf(f, w1.y - w0.y, w0.y); wq[e][2] = fmaf(f, w1.z - w0.z, w0.z);
+      aq[e][0] = fmaf(f, a1.x - a0.x, a0.x); aq[e][1] = fmaf(f, a1.y - a0.y, a0.y); aq[e][2] = fmaf(f, a1.z - a0.z, a0.z);
+    }
+    unsigned hit = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float s = j * (1.0f / 3.0f);
+      const float pt = fmaf(fmaf(s, wq[1][0] - wq[0][0], wq[0][0]), __expf(fmaf(s, aq[1][0] - aq[0][0], aq[0][0]) * gg1[j]),
+                            fmaf(fmaf(s, wq[1][1] - wq[0][1], wq[0][1]), __expf(fmaf(s, aq[1][1] - aq[0][1], aq[0][1]) * gg2[j]),
+                                 fmaf(s, wq[1][2] - wq[0][2], wq[0][2]) * __expf(fmaf(s, aq[1][2] - aq[0][2], aq[0][2]) * gg3[j])));
       if ((float)c[j] * 2.3283064365386963e-10f < pt) hit |= 1u << j;            // cond1: u < norm * ptot
     }
     if (!hit) continue;

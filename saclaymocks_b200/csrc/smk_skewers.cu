@@ -11,13 +11,6 @@
 
 #include "smk_internal.h"
 
-#ifndef SMK_SKEW_P
-#define SMK_SKEW_P 4
-#endif
-#ifndef SMK_SKEW_MINB
-#define SMK_SKEW_MINB 3
-#endif
-
 namespace smk {
 
 struct SkewerParams {
@@ -34,6 +27,7 @@ struct SkewerParams {
   float* delta_l;
   float* eta_par;
   float* vpar;
+  int pfd;                 // distance (rows of the window) of the L1 row prefetch
   int pf;                  // tuning bits: 1 = L2 prefetch of the next x slab of the window, 2 = L1 prefetch of the next row, 4 = L1 prefetch of the next x slab
 };
 
@@ -266,12 +260,17 @@ __device__ __forceinline__ void gather_multi2(const SkewerParams& p, const float
     }
     for (int b = 0; b < nyu; ++b) {
       const int lb = INTERIOR ? (by - DMAX + b) : min(max(by - DMAX + b, 0), p.ny - 1);
-      if (INTERIOR && (p.pf & 2) && b + 1 < nyu) {
-        const size_t nrow = (size_t)la * plane + (unsigned)(lb + 1) * (unsigned)p.nz + z0;
+      if (INTERIOR && (p.pf & 2)) {
+        // L1 prefetch of the window row p.pfd iterations ahead (wrapping into the next x slab)
+        int nb = b + p.pfd, na = a;
+        if (nb >= nyu) { nb -= nyu; ++na; }
+        if (na < nxu) {
+          const size_t nrow = (size_t)(la + (na - a)) * plane + (unsigned)(by - DMAX + nb) * (unsigned)p.nz + z0;
 #pragma unroll
-        for (int f = 0; f < NF; ++f) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow + WU - 1));
+          for (int f = 0; f < NF; ++f) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow + WU - 1));
+          }
         }
       }
       float2 wab2[P / 2];
@@ -555,6 +554,7 @@ extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const f
   p.qso = qso_xyzr; p.npix_forest = npix_forest; p.rvec = rvec;
   p.delta_l = delta_l; p.eta_par = eta_par; p.vpar = vpar;
   { const char* e = getenv("SMK_SKEW_PF"); p.pf = e ? atoi(e) : 2; }
+  { const char* e = getenv("SMK_SKEW_PFD"); p.pfd = e ? atoi(e) : 1; if (p.pfd < 1 || p.pfd > 7) p.pfd = 1; }
   // largest step between consecutive pixels of the grid (uniform 0.2 Mpc/h in the reference); decides whether the
   // register-blocked kernel may be used.  SMK_SKEWERS_SIMPLE=1 forces the one-pixel-per-thread kernel.
   double step = g->pixel_step;
