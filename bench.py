@@ -22,9 +22,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CHUNKS = {  # box size -> (ra0, dec0, half-width deg) of chunk 1, bin/submit_mocks.py:611-674
-    128: (190.0, 0.0, 1.6), 256: (189.982649735, 20.0, 3.17), 512: (190.0, 0.0, 6.4), 1024: (190.0, 0.0, 12.7),
-    2560: (125.5, 20.0, 32.2413248675)}
+def chunk_window(nx):
+    """(ra0, dec0, half-width deg) of chunk 1 for a box of nx cells: chunk_parameters() of bin/submit_mocks.py:611-674
+    (saclaymocks_b200/chunks.py); sizes outside its table (weak-scaling boxes) scale the 512-cell window."""
+    from saclaymocks_b200 import chunks
+    try:
+        ra0, dra, dec0, _ = chunks.chunk_window(nx, 1)
+        return ra0, dec0, dra
+    except ValueError:
+        return 190.0, 0.0, 6.4 * nx / 512.0
+
+
 QSO_DENSITY = 89.8          # per deg^2 for 1.8 < z < 3.6 from etc/nz_qso_desi.dat (SURVEY.md section 8d)
 DCELL = 2.19
 NZ = 1536
@@ -34,7 +42,7 @@ NZ = 1536
 def synthetic_qsos(nx, ny, seed=42):
     """Uniform in the chunk window, z from etc/nz_qso_desi.dat restricted to 1.8 < z < 3.6 (full density)."""
     from saclaymocks_b200 import tables
-    ra0, dec0, half = CHUNKS.get(nx, (190.0, 0.0, 6.4 * nx / 512.0))
+    ra0, dec0, half = chunk_window(nx)
     half_y = half * ny / nx
     rng = np.random.default_rng(seed)
     n = int(QSO_DENSITY * (2 * half) * (2 * half_y))
@@ -52,6 +60,14 @@ def weight_tables_device(bs, device):
     """The four spectral weight tables of this rank's k-slab, evaluated on the GPU from the P(k) splines
     (smk_pk_weights = GPU interpolate_pk; input preparation, outside the timed region)."""
     return {name: bs.weight_table(name) for name in ("Pln1", "Pln2", "Pln3", "P0")}
+
+
+WEAK_BOX = {1: (512, 512), 2: (1024, 512), 4: (1024, 1024), 8: (2048, 1024)}   # per-GPU cells fixed (weak scaling)
+
+
+def workload_name(nx, ny, nqso):
+    return ("single chunk %dx%dx%d: Philox noise + r2c + 13 products (3 lognormal, delta, 6 eta, 3 velocity) + %d "
+            "full-density skewers (gather 10 fields, delta_s, FGPA)" % (nx, ny, NZ, nqso))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -166,6 +182,9 @@ def run_reference(args):
         return
     cores = os.cpu_count()
     nx = 128
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    bx, by = (args.box, args.box) if args.box else WEAK_BOX.get(world, WEAK_BOX[1])
+    nqso = len(synthetic_qsos(bx, by)[0])
     vals, times = [], []
     for i in range(args.warmup + args.steps):
         t0 = time.time()
@@ -174,13 +193,15 @@ def run_reference(args):
             vals.append(r["value"])
             times.append(time.time() - t0)
     v = float(np.mean(vals))
-    sample = ("%dx%dx1536 box, 13 products (scipy.fft float32, workers=%d) + numba ReadSpec on 8 quasars/core "
-              "extrapolated to the box's full-density catalogue; pocketfft stands in for FFTW" % (nx, nx, cores))
+    sample = ("each step = a %dx%dx1536 box of the same workload: 13 products (scipy.fft float32, workers=%d) + numba "
+              "ReadSpec on 8 quasars/core extrapolated to that box's full-density catalogue; cells/s of the sample "
+              "stand for the workload's (FFT cost per cell grows only logarithmically with the box); pocketfft stands "
+              "in for FFTW (pyfftw is not installable)" % (nx, nx, cores))
     line = {"impl": "reference", "metric": "grf_cells_per_s", "value": v, "unit": "cells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "chunk: noise + r2c + 13 products + full-density skewers/FGPA, bounded sample",
-                       "box": [nx, nx, NZ]},
+            "config": {"workload": workload_name(bx, by, nqso), "box": [bx, by, NZ], "nqso": int(nqso),
+                       "sample_box": [nx, nx, NZ]},
             "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -205,13 +226,13 @@ def run_gpu(args):
     if args.box:
         nx = ny = args.box
     else:
-        nx, ny = {1: (512, 512), 2: (1024, 512), 4: (1024, 1024), 8: (2048, 1024)}[world]
+        nx, ny = WEAK_BOX[world]
     pipe = ChunkPipeline(nx, ny, NZ, DCELL, device=dev, rank=rank, nranks=world)
     W = weight_tables_device(pipe.bs, dev)
     ra, dec, z, ra0, dec0 = synthetic_qsos(nx, ny)
     pipe.set_catalogue(ra, dec, z, ra0, dec0)
     pipe.set_weights(W)
-    half = CHUNKS.get(nx, (190.0, 0.0, 6.4 * nx / 512.0))[2]
+    half = chunk_window(nx)[2]
     pipe.set_footprint(ra0, dec0, half, half * ny / nx)
     cells = nx * ny * NZ
 
@@ -259,9 +280,12 @@ def run_gpu(args):
     barrier()
     t_qso = 1e3 * (time.time() - tq) / max(1, min(args.steps, 3))
 
-    # ---- end-to-end arm: pinned host weights in, all boxes + all spectra rows back to host, every step
+    # ---- end-to-end arm: pinned host inputs in, all boxes + all spectra rows back to host, every step.  With several
+    #      ranks every rank stages its own x-slabs and rows over its own PCIe link; the time is taken between two
+    #      barriers (= the slowest rank) and the byte counts are summed over the ranks.
     e2e = None
-    if world == 1 and not args.no_e2e:
+    slab_bytes = pipe.bs.nxl * pipe.bs.NY * pipe.bs.NZ * 4
+    if not args.no_e2e and (slab_bytes <= (2 << 30) or args.e2e):
         host = pipe.make_host_buffers(W)
         pipe.step_e2e(host, seed=7)
         barrier()
@@ -271,9 +295,6 @@ def run_gpu(args):
             pipe.step_e2e(host, seed=8 + i)
         barrier()
         dt = (time.time() - t0) / n_e2e
-        e2e = {"value": cells / dt, "unit": "cells/s", "h2d_bytes_per_step": host["h2d_bytes"],
-               "d2h_bytes_per_step": host["d2h_bytes"], "ms_per_step": 1e3 * dt, "steps": n_e2e,
-               "skewer_pixels_per_s": npx / dt}
         pipe.step_e2e_resident(host, seed=7)
         barrier()
         t0 = time.time()
@@ -281,9 +302,21 @@ def run_gpu(args):
             pipe.step_e2e_resident(host, seed=8 + i)
         barrier()
         dtr = (time.time() - t0) / n_e2e
+        tt = torch.tensor([dt, dtr], dtype=torch.float64, device=dev)
+        bb = torch.tensor([host["h2d_bytes"], host["d2h_bytes"], 4 * pipe.out[0].numel() * 4 + 64 * nq_drawn],
+                          dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bb)
+        dt, dtr = (float(v) for v in tt.cpu())
+        h2d, d2h, d2h_res = (int(v) for v in bb.cpu())
+        e2e = {"value": cells / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * dt, "steps": n_e2e, "skewer_pixels_per_s": npx / dt,
+               "what": "P(k) splines + sightline catalogue in from pinned host memory (weight tables evaluated on the "
+                       "GPU inside the step), all 13 boxes and the four spectra arrays of every rank copied back to "
+                       "pinned host memory (PCIe-bound)"}
         e2e["resident"] = {"value": cells / dtr, "unit": "cells/s", "ms_per_step": 1e3 * dtr,
-                           "h2d_bytes_per_step": host["h2d_bytes"],
-                           "d2h_bytes_per_step": 4 * pipe.out[0].numel() * 4 + 64 * nq_drawn,
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_res,
                            "what": "same chunk with the boxes kept in HBM: P(k) splines + sightlines in, quasars drawn on "
                                    "the resident boxes (smk_draw_qso), quasar table + spectra rows out"}
         del host
@@ -326,10 +359,7 @@ def run_gpu(args):
         line = {"metric": "grf_cells_per_s", "value": world * cells / world / (t_tot * 1e-3), "unit": "cells/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_tot,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "single chunk %dx%dx%d: Philox noise + r2c + 13 products (3 lognormal, delta, "
-                                       "6 eta, 3 velocity) + %d full-density skewers (gather 10 fields, delta_s, FGPA)"
-                                       % (nx, ny, NZ, len(ra)),
-                           "box": [nx, ny, NZ], "nqso": int(len(ra)), "forest_pixels": int(npx),
+                "config": {"workload": workload_name(nx, ny, len(ra)), "box": [nx, ny, NZ], "nqso": int(len(ra)), "forest_pixels": int(npx),
                            "l2": "every pass streams >= 1.6 GB per launch, far above the 126 MB L2; no flush needed",
                            "parallelism": "x-slabs over %d GPU(s), all-to-all transposes" % world},
                 "grf_cells_per_s_boxes": cells / (t_box * 1e-3), "box_cells_per_s": 13 * cells / (t_box * 1e-3),
@@ -351,6 +381,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--box", type=int, default=0, help="NX=NY override (default: 512 per GPU, weak scaling)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e", action="store_true", help="run the end-to-end arm even when a rank's slab exceeds 2 GiB "
+                                                       "(two pinned staging buffers of that size per rank)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -288,7 +288,33 @@ class ChunkPipeline(object):
                                      [self.interior(k) for k in ("vx", "vy", "vz")] if self.rsd else None,
                                      ix0=self.rank * bs.nxl, uniforms=uniforms, seed=seed, chunk=fp["chunk"])
 
-    # ------------------------------------------------------------------ end-to-end through host buffers (1 GPU)
+    # ------------------------------------------------------------------ one chunk of the footprint, device resident
+    def run_chunk(self, chunk=1, seed=0, cells=None, stripe_footprint=False):
+        """The reference's per-chunk chain run_boxes-<c>.sh -> run_chunk-<c>.sh (submit_mocks.py:375-425: make_boxes,
+        draw_qso, make_spectra, merge_spectra) without the files in between: boxes of this chunk (seed as given to
+        make_boxes.py), quasars drawn on the resident lognormal boxes inside the chunk's window of chunk_parameters()
+        (Philox draws, THING_ID = chunk*1e9 + slab*1e6 + n + 1 as draw_qso.py:495), their sightlines through the
+        resident delta / eta / velocity boxes, small-scale field and FGPA.  Returns (catalogue of every rank's quasars
+        as a dict of numpy columns, (delta_l, eta_par, vpar, flux) device rows of the quasars whose sightline touches
+        this rank's slab -- row i belongs to catalogue entry self.cat["sel"][i])."""
+        from . import chunks
+        ra0, dra, dec0, ddec = chunks.chunk_window(cells if cells is not None else self.bs.NX, chunk, stripe_footprint)
+        self.set_footprint(ra0, dec0, dra, ddec, chunk=int(chunk))
+        self.step_boxes(seed)
+        mine = self.draw_qso(seed)
+        cols = ("RA", "DEC", "Z_QSO_NO_RSD", "Z_QSO_RSD", "HDU", "THING_ID")
+        parts = [{c: mine[c] for c in cols}]
+        if self.nranks > 1:                      # every rank needs the quasars of all slabs: a sightline crosses slabs
+            parts = [None] * self.nranks
+            torch.distributed.all_gather_object(parts, {c: mine[c] for c in cols}, group=self.group)
+        cat = {c: np.concatenate([p[c] for p in parts]) for c in cols}
+        z = cat["Z_QSO_RSD"] if self.rsd else cat["Z_QSO_NO_RSD"]              # make_spectra.py:417-420
+        self.set_catalogue(cat["RA"], cat["DEC"], z, ra0, dec0, ids=cat["THING_ID"])
+        self.step_skewers(seed)
+        return cat, self.out
+
+    # ------------------------------------------------------------------ end-to-end through host buffers
+    # (any number of ranks: every rank stages its own x-slab of each box and its own spectra rows over its own PCIe link)
     def make_host_buffers(self, W_dev):
         bs = self.bs
         from . import pk
@@ -299,12 +325,12 @@ class ChunkPipeline(object):
                      torch.empty(br.shape, dtype=torch.float64, device=self.device),
                      torch.empty(co.shape, dtype=torch.float64, device=self.device))
         host = {"pp": pp,
-                "box": [torch.empty((bs.NX, bs.NY, bs.NZ), dtype=torch.float32).pin_memory() for _ in range(2)],
+                "box": [torch.empty((bs.nxl, bs.NY, bs.NZ), dtype=torch.float32).pin_memory() for _ in range(2)],
                 "spec": [torch.empty(self.out[0].shape, dtype=torch.float32).pin_memory() for _ in range(4)],
                 "copy_stream": torch.cuda.Stream(device=self.device)}
         host["h2d_bytes"] = (sum(v[0].numel() * 8 + v[1].numel() * 8 for v in pp.values()) + self.cat["xyzr"].nbytes
                              + self.cat["nfor"].nbytes)
-        host["d2h_bytes"] = len(PRODUCTS) * bs.NX * bs.NY * bs.NZ * 4 + 4 * self.out[0].numel() * 4
+        host["d2h_bytes"] = len(PRODUCTS) * bs.nxl * bs.NY * bs.NZ * 4 + 4 * self.out[0].numel() * 4
         return host
 
     def step_e2e_resident(self, host, seed=0):
@@ -312,7 +338,7 @@ class ChunkPipeline(object):
         drawn on the resident boxes (smk_draw_qso, Philox draws) and only the quasar table and the spectra rows go back
         to the host -- no box ever crosses PCIe.  (The skewers use the catalogue given to set_catalogue so that the
         workload is the one `value` is quoted on.)"""
-        assert self.nranks == 1 and self.footprint is not None
+        assert self.footprint is not None
         main = torch.cuda.current_stream(self.device)
         cs = host["copy_stream"]
         self.stats.zero_()
@@ -340,8 +366,9 @@ class ChunkPipeline(object):
     def step_e2e(self, host, seed=0):
         """Host inputs in (P(k) splines and the quasar catalogue, pinned), every box and every spectrum row out to
         host memory.  The spectral weight tables are evaluated on the GPU (smk_pk_weights) inside the step.  The two
-        pinned box buffers stand for the FITS writer's staging area; copies overlap the next product's transforms."""
-        assert self.nranks == 1
+        pinned box buffers stand for the FITS writer's staging area; copies overlap the next product's transforms.
+        With several ranks each product goes through the serial NCCL exchange (forward()/product()): the step is bound
+        by the PCIe copies of the slabs, which run on every rank's own link."""
         main = torch.cuda.current_stream(self.device)
         cs = host["copy_stream"]
         self.stats.zero_()

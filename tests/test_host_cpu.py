@@ -133,3 +133,24 @@ def test_reference_arm_of_bench_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "grf_cells_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_chunk_parameters_match_the_reference_table():
+    """saclaymocks_b200.chunks.chunk_parameters against the unmodified submit_mocks.py:611-674 (fixture written by
+    tests/golden/make_ref_chunks.py): same strings, same order, same slab counts, for every box size and the stripe
+    footprint; chunk 1 of the nominal box and the C1 / C2 windows of SURVEY.md section 8d as floats."""
+    from saclaymocks_b200 import chunks
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_chunks.json")))
+    assert len(g) == 12
+    for key, v in g.items():
+        cells, stripe = (int(t) for t in key.split("_"))
+        ra0, dra, dec0, ddec, cid, nslice = chunks.chunk_parameters(cells, bool(stripe))
+        for name, arr in (("ra0", ra0), ("dra", dra), ("dec0", dec0), ("ddec", ddec), ("chunkid", cid)):
+            assert isinstance(arr, np.ndarray) and arr.dtype.kind == "U" and list(arr) == v[name], (key, name)
+        assert int(nslice) == v["nslice"] and nslice.shape == ()
+    assert chunks.chunk_ids(2560) == [1, 2, 3, 4, 5, 6, 7]
+    assert chunks.chunk_window(2560, 1) == (125.5, 32.2413248675, 20.0, 32.2413248675)
+    assert chunks.chunk_window(256, 1) == (189.982649735, 3.17, 20.0, 3.17)
+    assert chunks.chunk_window(512, 6) == (202.8, 6.4, 12.8, 6.4)
+    with pytest.raises(ValueError):
+        chunks.chunk_parameters(100)
