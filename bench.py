@@ -332,9 +332,8 @@ def run_gpu(args):
     achieved = alg[dom] / (per[dom] * 1e-3) / 1e9 if per[dom] else 0.0
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (512 x 512 x 1536 only)
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "traffic_r01b.json")
-    if not os.path.isfile(tfile):
-        tfile = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    tfile = next((f for f in (os.path.join(ROOT, "profiles", "traffic_%s.json" % t) for t in ("r01d", "r01b", "r01"))
+                  if os.path.isfile(f)), "")
     if os.path.isfile(tfile) and (nx, ny, world) == (512, 512, 1):
         tj = json.load(open(tfile))
         key = {"c2r_z": "c2r_z_kernel<768>", "inv_y": "c2c_strided_kernel<512, 1, 0, 0, 0>",

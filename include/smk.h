@@ -167,7 +167,8 @@ int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], 
 
 /* ---- small-scale field (merge_spectra.py:308-324): delta_s = irfft(rfft(noise) * filt)[:npix] * zscale.
  * noise: [nqso][nfft] float white noise, or NULL to draw Philox(seed, quasar index).  filt_rows: [nrows][nfft/2+1]
- * float = sqrt(max(P_miss(z_row,k),0)/pixsize); row_of_qso[q] selects the row (nearest tabulated z to z_eff).
+ * float = sqrt(max(P_miss(z_row,k),0)/pixsize); row_of_qso[q] selects the row (nearest tabulated z to z_eff); a
+ * negative row marks an empty forest, whose delta_s row is set to 0 (merge_spectra.py:327-330).
  * zscale: [nqso][npix] or NULL; when NULL, sig_pix[npix]/sig_eff[q] is used (sigma_s(z)/sigma_s(z_eff)).
  * qso_ids: [nqso] Philox stream id of each quasar (NULL: the row index), so that every rank that holds a piece of
  * a sightline regenerates the same delta_s.  nfft must be a power of two in [256, 8192]. */

@@ -20,6 +20,9 @@
 #ifndef SMK_MID_LINES
 #define SMK_MID_LINES 16  // kz columns per tile for x/y lengths 512 and 1024
 #endif
+#ifndef SMK_LINES_1024
+#define SMK_LINES_1024 SMK_MID_LINES
+#endif
 #ifndef SMK_BIG_LINES
 #define SMK_BIG_LINES 8   // kz columns per tile for x/y lengths above 1024 (shared memory: N * LINES * 8 B)
 #endif
@@ -29,14 +32,17 @@ namespace smk {
 // ------------------------------------------------------------------ strided complex pass
 template <int N>
 struct StridedTraits {
-  static constexpr int LINES = (N > 1024) ? SMK_BIG_LINES : (N >= 512 ? SMK_MID_LINES : 16);
+  static constexpr int LINES = (N > 1024) ? SMK_BIG_LINES : (N == 1024 ? SMK_LINES_1024 : (N >= 512 ? SMK_MID_LINES : 16));
   static constexpr int NT_ = LINES * N / 32;
   // 2560 = 16*16*2*5: 640 threads give 2 radix-16 butterflies per thread and stage (64 + 32 registers of payload)
   static constexpr int NT = (N == 2560) ? 640 : (NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_));
   // resident CTAs per SM the register allocation should allow (shared memory: N*LINES*8 B per CTA)
   static constexpr int SMEM = N * LINES * 8;
   static constexpr int MINB_ = 220 * 1024 / SMEM;
-  static constexpr int MINB = MINB_ < 1 ? 1 : (MINB_ * NT > 1536 ? 1536 / NT : MINB_);
+  static constexpr int MINB__ = MINB_ < 1 ? 1 : (MINB_ * NT > 1536 ? 1536 / NT : MINB_);
+  // a radix-32 first stage holds 64 payload registers per thread: at most 2 CTAs of 256 threads per SM (128 registers)
+  static constexpr bool BIG_R0 = PlanFor<N>::type::radix(0) >= 32;
+  static constexpr int MINB = (BIG_R0 && MINB__ * NT > 512) ? (512 / NT < 1 ? 1 : 512 / NT) : MINB__;
 };
 
 struct StridedParams {
@@ -72,9 +78,10 @@ enum { OUT_PLAIN = 0, OUT_SPLIT = 1, OUT_PEER = 2 };
 #endif
 
 template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
-__global__ void __launch_bounds__(StridedTraits<N>::NT, (MUL != MUL_TABLE || StridedTraits<N>::MINB == 1)
-                                                              ? StridedTraits<N>::MINB
-                                                              : StridedTraits<N>::MINB - 1)
+__global__ void __launch_bounds__(StridedTraits<N>::NT,
+                                  (MUL != MUL_TABLE || StridedTraits<N>::MINB == 1 || StridedTraits<N>::BIG_R0)
+                                      ? StridedTraits<N>::MINB
+                                      : StridedTraits<N>::MINB - 1)
     c2c_strided_kernel(const __grid_constant__ StridedParams p) {
   using P = typename PlanFor<N>::type;
   constexpr int LINES = StridedTraits<N>::LINES;

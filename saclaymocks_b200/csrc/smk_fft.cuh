@@ -310,11 +310,40 @@ SMK_PLAN(96, 8, 4, 3)
 SMK_PLAN(128, 8, 4, 4)
 SMK_PLAN(256, 16, 16)
 SMK_PLAN(384, 8, 4, 4, 3)
+// 512 and 1024 run as two-stage plans with a radix-32 first stage: a strided pass then touches shared memory twice
+// per element (first stage writes, last stage reads) instead of four times, loads half the twiddles and has one
+// barrier less, at 64 payload registers per thread (2 CTAs of 256 threads per SM).  Measured on B200 against the
+// three-stage plans 8.8.8 / 16.16.4 (-DSMK_PLAN_512=3 -DSMK_PLAN_1024=3, tools/plan_sweep.sh): 512-point passes
+// y 0.616 -> 0.572 ms, x with table 0.854 -> 0.762 ms, forward y 0.646 -> 0.523 ms; 1024-point passes y 3.40 -> 2.85 ms,
+// x with k-factors 3.51 -> 3.00 ms (x with table 4.83 -> 5.04 ms: the 32 weights spill at 128 registers).
+#ifndef SMK_PLAN_512
+#define SMK_PLAN_512 2
+#endif
+#ifndef SMK_PLAN_1024
+#define SMK_PLAN_1024 2
+#endif
+#if SMK_PLAN_512 == 2
+SMK_PLAN(512, 32, 16)
+#else
 SMK_PLAN(512, 8, 8, 8)
+#endif
 SMK_PLAN(768, 16, 16, 3)
+#if SMK_PLAN_1024 == 2
+SMK_PLAN(1024, 32, 32)
+#else
 SMK_PLAN(1024, 16, 16, 4)
+#endif
 SMK_PLAN(2048, 16, 16, 8)
+#ifndef SMK_PLAN_2560
+#define SMK_PLAN_2560 4
+#endif
+#if SMK_PLAN_2560 == 3
+SMK_PLAN(2560, 32, 16, 5)
+#elif SMK_PLAN_2560 == 31
+SMK_PLAN(2560, 16, 32, 5)
+#else
 SMK_PLAN(2560, 16, 16, 2, 5)
+#endif
 SMK_PLAN(4096, 16, 16, 16)
 #undef SMK_PLAN
 

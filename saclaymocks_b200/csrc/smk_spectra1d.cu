@@ -24,34 +24,59 @@ struct SmallScaleParams {
   const float2* tw;        // W_nfft
 };
 
+// All stages of plan P on the single line of the CTA through the (padded) load/store functors; the last stage
+// re-sorts its outputs to natural order in place.  A barrier follows every stage.
+template <class P, int S0, bool INV, int NT, class Load, class Store>
+__device__ __forceinline__ void ss_fft(Load ld, Store st, const float2* __restrict__ tw) {
+  if constexpr (S0 < P::S - 1) {
+    dif_stage<P, S0, INV, 1, NT, OUT_INPLACE>(ld, st, tw, 2);
+    __syncthreads();
+    ss_fft<P, S0 + 1, INV, NT>(ld, st, tw);
+  } else {
+    dif_stage<P, P::S - 1, INV, 1, NT, OUT_RESORT>(ld, st, tw, 2);
+    __syncthreads();
+  }
+}
+
+// Shared-memory index of point p of the single line a CTA transforms: one float2 of padding after every 16 points.
+// With one line per CTA the lanes of a warp run DIFFERENT butterflies, so the last radix-16 stage reads points
+// 16 b + t for consecutive b: unpadded that is a 128-byte stride (all lanes on one bank pair, a 16-way conflict; the
+// first version spent 85 % of its time in those replays); padded it is a 17-float2 stride, conflict free.
+__device__ __forceinline__ int ss_idx(int p) { return p + (p >> 4); }
+
 template <int M>
 __global__ void __launch_bounds__(M >= 2048 ? 512 : (M >= 512 ? 256 : 64)) smallscale_kernel(SmallScaleParams p) {
   using P = typename PlanFor<M>::type;
   constexpr int NT = M >= 2048 ? 512 : (M >= 512 ? 256 : 64);
-  constexpr int LP = M + 1;
-  extern __shared__ float2 sm[];   // [M+1]
+  extern __shared__ float2 sm[];   // [M + M/16 + 1]
   const int q = blockIdx.x;
   const int nfft = 2 * M;
+  const int frow = p.row_of_qso[q];
+  if (frow < 0) {                  // empty forest: delta_s = 0 (merge_spectra.py:327-330)
+    for (int i = threadIdx.x; i < p.npix; i += NT) p.delta_s[(size_t)q * p.npix + i] = 0.f;
+    return;
+  }
+  auto ld = [&](int, int pos, int, int) { return sm[ss_idx(pos)]; };
+  auto st = [&](int, int pos, float2 val) { sm[ss_idx(pos)] = val; };
   // ---- white noise as M float2
   if (p.noise) {
     const float2* in2 = reinterpret_cast<const float2*>(p.noise + (size_t)q * nfft);
-    for (int n = threadIdx.x; n < M; n += NT) sm[n] = __ldg(in2 + n);
+    for (int n = threadIdx.x; n < M; n += NT) sm[ss_idx(n)] = __ldg(in2 + n);
   } else {
     for (int c = threadIdx.x; c < M / 2; c += NT) {
       uint64_t id = p.ids ? (uint64_t)p.ids[q] : (uint64_t)q;
       float4 g = philox_normal4(p.seed ^ 0x5ca1ab1e5eedULL, id * (uint64_t)(M / 2) + c);
-      sm[2 * c] = make_float2(g.x, g.y);
-      sm[2 * c + 1] = make_float2(g.z, g.w);
+      sm[ss_idx(2 * c)] = make_float2(g.x, g.y);
+      sm[ss_idx(2 * c + 1)] = make_float2(g.z, g.w);
     }
   }
   __syncthreads();
-  // ---- forward r2c
-  dif_stages_smem<P, 0, P::S - 1, false, 1, LP, 1, NT>(sm, p.tw, 2);
-  dif_last_resort_smem<P, false, 1, LP, 1, NT>(sm, p.tw, 2);
-  const float* filt = p.filt + (size_t)p.row_of_qso[q] * (M + 1);
+  // ---- forward r2c: M-point complex FFT of z[n] = x[2n] + i x[2n+1], output re-sorted to natural order
+  ss_fft<P, 0, false, NT>(ld, st, p.tw);
+  const float* filt = p.filt + (size_t)frow * (M + 1);
   // ---- post-process to X[k], multiply by the filter, and pre-process for the inverse, pair (k, M-k) at a time
   for (int k = threadIdx.x; k <= M / 2; k += NT) {
-    float2 a = sm[k], b = (k == 0) ? a : sm[M - k];
+    float2 a = sm[ss_idx(k)], b = (k == 0) ? a : sm[ss_idx(M - k)];
     float2 w = __ldg(p.tw + k);
     float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
     float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
@@ -68,18 +93,17 @@ __global__ void __launch_bounds__(M >= 2048 ? 512 : (M >= 512 ? 256 : 64)) small
     float2 wc = make_float2(w.x, -w.y);
     float2 A = make_float2(xk.x + xm.x, xk.y - xm.y);
     float2 B = cmul(make_float2(xk.x - xm.x, xk.y + xm.y), wc);
-    sm[k] = make_float2(A.x - B.y, A.y + B.x);
-    if (k != 0 && k != M - k) sm[M - k] = make_float2(A.x + B.y, -A.y + B.x);
+    sm[ss_idx(k)] = make_float2(A.x - B.y, A.y + B.x);
+    if (k != 0 && k != M - k) sm[ss_idx(M - k)] = make_float2(A.x + B.y, -A.y + B.x);
   }
   __syncthreads();
-  dif_stages_smem<P, 0, P::S - 1, true, 1, LP, 1, NT>(sm, p.tw, 2);
-  dif_last_resort_smem<P, true, 1, LP, 1, NT>(sm, p.tw, 2);
+  ss_fft<P, 0, true, NT>(ld, st, p.tw);
   // ---- numpy's irfft normalises by 1/nfft; keep the first npix samples; z-dependence of sigma_s
   const float inv_n = 1.0f / (float)nfft;
   const float se = p.sig_eff ? 1.0f / p.sig_eff[q] : 1.0f;
   const float* sm_f = reinterpret_cast<const float*>(sm);
   for (int i = threadIdx.x; i < p.npix; i += NT) {
-    float v = (i < nfft) ? sm_f[i] * inv_n : 0.f;
+    float v = (i < nfft) ? sm_f[2 * ss_idx(i >> 1) + (i & 1)] * inv_n : 0.f;
     if (p.sig_pix) v *= p.sig_pix[i] * se;
     p.delta_s[(size_t)q * p.npix + i] = v;
   }
@@ -88,7 +112,7 @@ __global__ void __launch_bounds__(M >= 2048 ? 512 : (M >= 512 ? 256 : 64)) small
 template <int M>
 static int launch_smallscale_t(const SmallScaleParams& p, cudaStream_t st) {
   constexpr int NT = M >= 2048 ? 512 : (M >= 512 ? 256 : 64);
-  size_t smem = (size_t)(M + 1) * sizeof(float2);
+  size_t smem = (size_t)(M + M / 16 + 1) * sizeof(float2);
   smallscale_kernel<M><<<p.nqso, NT, smem, st>>>(p);
   SMK_CUDA_OK(cudaGetLastError());
   return SMK_OK;

@@ -194,9 +194,7 @@ class FGPA(object):
             assert tuple(nz_t.shape) == (nq, nfft)
         _lib.check(self.lib.smk_smallscale(None, nq, nfft, npix, _ptr(nz_t), C.c_uint64(seed), _ptr(self.filt_rows(nfft)),
                                            _ptr(rows_t), _ptr(self.sig_pix), _ptr(sig_eff_t), _ptr(ids_t), _ptr(d)))
-        if empty is not None:
-            d[empty] = 0
-        return d
+        return d                  # rows of empty forests are zeroed by the kernel (row_of_qso = -1)
 
     def prepare(self, nforest, qso_ids=None):
         """Per-quasar inputs of the small-scale kernel: P1D_miss table row (nearest tabulated z to z_eff), sigma_s(z_eff),
@@ -209,6 +207,8 @@ class FGPA(object):
         ids_t = None if qso_ids is None else torch.as_tensor(np.asarray(qso_ids, dtype=np.int64), device=self.device)
         em = np.asarray(nforest) <= 0
         empty = torch.as_tensor(em, device=self.device) if em.any() else None
+        if em.any():
+            rows_t[empty] = -1         # smk_smallscale writes delta_s = 0 for these (merge_spectra.py:327-330)
         return rows_t, sig_eff_t, ids_t, empty
 
     def flux(self, delta_l, delta_s=None, eta_par=None):

@@ -169,6 +169,6 @@ def test_run_chunk_resident_chain(cuda):
         if m.any():
             assert np.max(np.abs(dl[row, idx][m] - p["delta_l"][m])) < 1e-5
             f = F[row, idx][m]
-            assert np.all((f > 0) & (f <= 1))
+            assert np.all((f >= 0) & (f <= 1))           # float32 F underflows to 0 in dense absorbers
             checked += int(m.sum())
     assert checked > 1000
