@@ -71,7 +71,10 @@ class ChunkPipeline(object):
             _lib.check(L.smk_exchange_connect(h, b, blob))
         self._xptr = [L.smk_exchange_ptr(h, b) for b in range(2)]
         self._tok = torch.zeros(1, dtype=torch.float32, device=self.device)
-        self._xstream = torch.cuda.Stream(device=self.device)
+        # SMK_X_SMS > 0: the x pass runs persistent on that many CTAs (libsmk) and on a high-priority stream, so that
+        # its CTAs are placed first and the y / z passes of the other stream fill the remaining SMs
+        prio = -1 if int(os.environ.get("SMK_X_SMS", "0") or 0) > 0 else 0
+        self._xstream = torch.cuda.Stream(device=self.device, priority=prio)
         dist.barrier(group=self.group)
 
     def _stream_barrier(self):

@@ -57,6 +57,7 @@ struct StridedParams {
   // buffer, already offset to this rank's chunk) at (k % nsplit) * lo_stride + outer * outer_stride + column
   float2* peer[SMK_MAX_RANKS];
   int pf_dist;   // L2 prefetch distance in tiles (0 = off): each CTA prefetches the input rows of tile id + pf_dist
+  int nouter;    // tiles = (ncols / LINES) x nouter
 };
 
 // element offset of point n: plain stride, or the two-level [hi][lo] form left behind by an all-to-all
@@ -77,12 +78,9 @@ enum { OUT_PLAIN = 0, OUT_SPLIT = 1, OUT_PEER = 2 };
 #define SMK_MUL_BATCH 2   // first-stage tasks loaded together in the k-factor passes (0 = all)
 #endif
 
+// One tile (LINES kz columns x N points) of a strided pass: column tile tile_x of outer index `outer`.
 template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
-__global__ void __launch_bounds__(StridedTraits<N>::NT,
-                                  (MUL != MUL_TABLE || StridedTraits<N>::MINB == 1 || StridedTraits<N>::BIG_R0)
-                                      ? StridedTraits<N>::MINB
-                                      : StridedTraits<N>::MINB - 1)
-    c2c_strided_kernel(const __grid_constant__ StridedParams p) {
+__device__ __forceinline__ void strided_tile(const StridedParams& p, const int tile_x, const int outer) {
   using P = typename PlanFor<N>::type;
   constexpr int LINES = StridedTraits<N>::LINES;
   constexpr int NT = StridedTraits<N>::NT;
@@ -91,8 +89,7 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT,
   constexpr int B0 = (MUL == MUL_NONE || MUL == MUL_TABLE || P::S == 1) ? 0 : SMK_MUL_BATCH;   // first-stage batch
   constexpr int TPT0 = (B0 > 0 && B0 < TPT0_ALL) ? B0 : TPT0_ALL;
   extern __shared__ float2 sm[];   // [N][LINES]
-  const int col = blockIdx.x * LINES + threadIdx.x % LINES;   // this thread's kz column (fixed for the kernel)
-  const int outer = blockIdx.y;
+  const int col = tile_x * LINES + threadIdx.x % LINES;   // this thread's kz column (fixed for the tile)
   const long long in_col = p.ain.tile_width ? (long long)(col / p.ain.tile_width) * p.ain.tile_stride + col % p.ain.tile_width
                                             : (long long)col;
   const float2* __restrict__ inl = p.in + (outer * p.ain.outer_stride + in_col);
@@ -100,9 +97,10 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT,
   if (!SPLIT_IN && p.pf_dist > 0) {
     // The first stage exposes one full DRAM latency per CTA (60 % of the kernel in the ncu source view).  Pull the
     // rows (one 128-B line each when LINES == 16) of the tile a later CTA will read into L2 now.
-    const long long id = (long long)blockIdx.y * gridDim.x + blockIdx.x + p.pf_dist;
-    const int ty = (int)(id / gridDim.x), tx = (int)(id - (long long)ty * gridDim.x);
-    if (ty < (int)gridDim.y) {
+    const int gx = p.ncols / LINES;
+    const long long id = (long long)outer * gx + tile_x + p.pf_dist;
+    const int ty = (int)(id / gx), tx = (int)(id - (long long)ty * gx);
+    if (ty < p.nouter) {
       const float2* nxt = p.in + ((long long)ty * p.ain.outer_stride + (long long)tx * LINES);
       for (int n = threadIdx.x; n < N; n += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + n * p.ain.lo_stride));
       if (MUL == MUL_TABLE) {
@@ -173,7 +171,7 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT,
     }
     __syncthreads();
     const int per_dest = p.aout.nsplit * (LINES / 2);                       // float4 per destination block
-    const long long doff = blockIdx.x * p.aout.tile_stride + outer * p.aout.outer_stride;
+    const long long doff = tile_x * p.aout.tile_stride + outer * p.aout.outer_stride;
     const float4* sm4 = reinterpret_cast<const float4*>(sm);
     for (int d = 0; d < N / p.aout.nsplit; ++d) {
       float4* dst = reinterpret_cast<float4*>(p.peer[d] + doff);
@@ -190,6 +188,48 @@ __global__ void __launch_bounds__(StridedTraits<N>::NT,
   }
 }
 
+#define SMK_STRIDED_BOUNDS(N, MUL)                                                                        \
+  __launch_bounds__(StridedTraits<N>::NT,                                                                 \
+                    (MUL != MUL_TABLE || StridedTraits<N>::MINB == 1 || StridedTraits<N>::BIG_R0)        \
+                        ? StridedTraits<N>::MINB                                                          \
+                        : StridedTraits<N>::MINB - 1)
+
+// one CTA per tile: grid (ncols / LINES, nouter)
+template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
+__global__ void SMK_STRIDED_BOUNDS(N, MUL) c2c_strided_kernel(const __grid_constant__ StridedParams p) {
+  strided_tile<N, INV, MUL, SPLIT_IN, SPLIT_OUT>(p, blockIdx.x, blockIdx.y);
+}
+
+// Persistent form for the fused-exchange x pass: a 1-D grid of SMK_X_SMS CTAs walks the tiles.  That pass is bound by
+// NVLink, not by the SMs; capping its grid leaves the other SMs to the y / z passes of the previous product, which run
+// on the second stream (with one CTA per tile the pass floods every SM and the two streams only time-slice, DESIGN.md
+// section 6).  The tile body is called out of line so that its register allocation stays that of the plain kernel.
+template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
+__device__ __noinline__ void strided_tile_call(const StridedParams& p, int tile_x, int outer) {
+  strided_tile<N, INV, MUL, SPLIT_IN, SPLIT_OUT>(p, tile_x, outer);
+}
+template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
+__global__ void SMK_STRIDED_BOUNDS(N, MUL) c2c_strided_persistent_kernel(const __grid_constant__ StridedParams p) {
+  const int gx = p.ncols / StridedTraits<N>::LINES;
+  const int ntiles = gx * p.nouter;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    strided_tile_call<N, INV, MUL, SPLIT_IN, SPLIT_OUT>(p, tile % gx, tile / gx);
+    __syncthreads();   // the next tile reuses the shared-memory tile
+  }
+}
+
+// CTAs of the persistent fused-exchange x pass (SMK_X_SMS, 0 = one CTA per tile)
+static int peer_grid_cap() {
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("SMK_X_SMS");
+    cap = e ? atoi(e) : 0;
+    if (cap < 0) cap = 0;
+  }
+  return cap;
+}
+
 template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
 static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st) {
   constexpr int LINES = StridedTraits<N>::LINES;
@@ -199,6 +239,16 @@ static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st)
   if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (p.ncols % LINES) { set_error("strided pass: column count must be a multiple of the tile width"); return SMK_ERR_ARG; }
   dim3 grid(p.ncols / LINES, nouter);
+  if constexpr (SPLIT_OUT == OUT_PEER) {
+    const int cap = peer_grid_cap();
+    if (cap > 0 && (long long)cap < (long long)grid.x * grid.y) {
+      auto pkern = c2c_strided_persistent_kernel<N, INV, MUL, SPLIT_IN, SPLIT_OUT>;
+      if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pkern<<<cap, NT, smem, st>>>(p);
+      SMK_CUDA_OK(cudaGetLastError());
+      return SMK_OK;
+    }
+  }
   kern<<<grid, NT, smem, st>>>(p);
   SMK_CUDA_OK(cudaGetLastError());
   return SMK_OK;
@@ -267,7 +317,7 @@ int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, floa
                        float2* const* peers, int npeers) {
   make_fastdiv(ain);
   make_fastdiv(aout);
-  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw, {nullptr}, prefetch_distance()};
+  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw, {nullptr}, prefetch_distance(), nouter};
   if (peers) {
     if (npeers > SMK_MAX_RANKS) { set_error("too many ranks for the fused exchange"); return SMK_ERR_ARG; }
     for (int i = 0; i < npeers; ++i) p.peer[i] = peers[i];

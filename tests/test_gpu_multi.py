@@ -12,13 +12,15 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, port, shape, dcell, out, p2p):
+def _worker(rank, world, port, shape, dcell, out, p2p, xsms=0):
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, HERE)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["SMK_P2P"] = p2p
+    if xsms:
+        os.environ["SMK_X_SMS"] = str(xsms)      # persistent fused-exchange x pass on that many CTAs
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -78,16 +80,18 @@ def _worker(rank, world, port, shape, dcell, out, p2p):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shape,p2p", [(2, (32, 32, 96), "auto"), (2, (64, 32, 96), "0"), (2, (2048, 32, 96), "1"),
-                                             (4, (64, 64, 96), "auto")])
-def test_sharded_pipeline_matches_oracle(tmp_path, world, shape, p2p):
-    """p2p: "1" = fused peer-store exchange (tiled receive layout), "0" = NCCL all-to-all, "auto" = by size."""
+@pytest.mark.parametrize("world,shape,p2p,xsms", [(2, (32, 32, 96), "auto", 0), (2, (64, 32, 96), "0", 0),
+                                                  (2, (2048, 32, 96), "1", 0), (4, (64, 64, 96), "auto", 0),
+                                                  (2, (64, 32, 96), "1", 3), (2, (2048, 32, 96), "1", 5)])
+def test_sharded_pipeline_matches_oracle(tmp_path, world, shape, p2p, xsms):
+    """p2p: "1" = fused peer-store exchange (tiled receive layout), "0" = NCCL all-to-all, "auto" = by size;
+    xsms > 0: the fused x pass runs persistent on that many CTAs (SMK_X_SMS), several tiles per CTA."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     out = str(tmp_path / "res")
-    port = 29600 + world + shape[0]
-    mp.spawn(_worker, args=(world, port, shape, 3364.0 / shape[2], out, p2p), nprocs=world, join=True)
+    port = 29600 + world + shape[0] + 7 * xsms
+    mp.spawn(_worker, args=(world, port, shape, 3364.0 / shape[2], out, p2p, xsms), nprocs=world, join=True)
     pieces = 0
     for r in range(world):
         import json
