@@ -334,11 +334,41 @@ int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, floa
 // ------------------------------------------------------------------ contiguous (z) pass
 template <int M>
 struct ZTraits {
+  using P = typename PlanFor<M>::type;
   static constexpr int LINES = (M > 1024) ? 4 : 16;
   static constexpr int NT_ = (M % 3 == 0) ? LINES * M / 48 / 32 * 32 : LINES * M / 32;
   static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
-  static constexpr int LP = M + 1;   // odd pitch: column accesses (lane = line) are conflict free
+  // PERM: two-stage plan R0.R1 with a radix-32 first stage, run without the re-sorting last stage (which would need
+  // all of a thread's butterflies in registers at once).  Natural index k then sits at position (k % R0) R1 + k / R0;
+  // with one float2 of padding after every R1 points, consecutive k are 25 float2 apart for R1 = 24: the permuted
+  // reads of the store / post-processing loops (lane = k) stay free of bank conflicts.
+  static constexpr bool PERM = (P::S == 2 && P::radix(0) >= 32);
+  static constexpr int R0 = P::radix(0), R1 = PERM ? P::radix(1) : 1;
+  static constexpr int LP_ = PERM ? M + M / R1 : M;
+  static constexpr int LP = LP_ + 1 - LP_ % 2;   // odd pitch: column accesses (lane = line) are conflict free
+  __device__ static __forceinline__ int idx(int p) { return PERM ? p + p / R1 : p; }         // padded position
+  __device__ static __forceinline__ int nat(int k) { return PERM ? idx((k % R0) * R1 + k / R0) : k; }   // where output k sits
 };
+
+// the M-point transform of every line of the tile in shared memory ([line][idx(point)], pitch LP); natural-order input.
+// Output k of a line ends at ZTraits<M>::nat(k).
+template <int M, bool INV>
+__device__ __forceinline__ void z_tile_fft(float2* sm, const float2* __restrict__ tw) {
+  using ZT = ZTraits<M>;
+  using P = typename ZT::P;
+  constexpr int LINES = ZT::LINES, NT = ZT::NT, LP = ZT::LP;
+  if constexpr (ZT::PERM) {
+    auto ld = [&](int line, int pos, int, int) { return sm[line * LP + ZT::idx(pos)]; };
+    auto st = [&](int line, int pos, float2 val) { sm[line * LP + ZT::idx(pos)] = val; };
+    dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 1>(ld, st, tw, 2);
+    __syncthreads();
+    dif_stage<P, 1, INV, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 1>(ld, st, tw, 2);
+    __syncthreads();
+  } else {
+    dif_stages_smem<P, 0, P::S - 1, INV, LINES, LP, 1, NT>(sm, tw, 2);
+    dif_last_resort_smem<P, INV, LINES, LP, 1, NT>(sm, tw, 2);
+  }
+}
 
 struct R2CParams {
   const float* in;
@@ -352,7 +382,7 @@ struct R2CParams {
 
 template <int M, bool PHILOX>
 __global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
-  using P = typename PlanFor<M>::type;
+  using ZT = ZTraits<M>;
   constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = ZTraits<M>::LP;
   extern __shared__ float2 sm[];   // [LINES][LP]
   const long long line0 = (long long)blockIdx.x * LINES;
@@ -364,8 +394,8 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
       if (line0 + line < p.nlines) {
         long long cell = p.cell0 + (line0 + line) * (2LL * M) + 4LL * c;
         float4 g = philox_normal4(p.seed, (uint64_t)cell >> 2);
-        sm[line * LP + 2 * c] = make_float2(g.x, g.y);
-        sm[line * LP + 2 * c + 1] = make_float2(g.z, g.w);
+        sm[line * LP + ZT::idx(2 * c)] = make_float2(g.x, g.y);
+        sm[line * LP + ZT::idx(2 * c + 1)] = make_float2(g.z, g.w);
       }
     }
   } else {
@@ -374,14 +404,13 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
       if (line0 + line < p.nlines) {
         const float2* src = in2 + (line0 + line) * M;
 #pragma unroll 8
-        for (int n = threadIdx.x & 31; n < M; n += 32) sm[line * LP + n] = __ldg(src + n);
+        for (int n = threadIdx.x & 31; n < M; n += 32) sm[line * LP + ZT::idx(n)] = __ldg(src + n);
       }
     }
   }
   __syncthreads();
   // ---- M-point complex FFT of z[n] = x[2n] + i x[2n+1], output re-sorted to natural order
-  dif_stages_smem<P, 0, P::S - 1, false, LINES, LP, 1, NT>(sm, p.tw, 2);
-  dif_last_resort_smem<P, false, LINES, LP, 1, NT>(sm, p.tw, 2);
+  z_tile_fft<M, false>(sm, p.tw);
   // ---- store with the real-transform post-step fused in: X[k] = (Z[k]+conj(Z[M-k]))/2 - (i/2) w^k (Z[k]-conj(Z[M-k]))
   //      for the pair (k, M-k); one warp per line, both global writes coalesced; row pads are zeroed so that later
   //      passes may stream whole rows
@@ -391,7 +420,7 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
       float2* dst = p.out + (line0 + line) * p.pitch;
 #pragma unroll 4
       for (int k = threadIdx.x & 31; k <= M / 2; k += 32) {
-        float2 a = row[k], b = (k == 0) ? a : row[M - k];
+        float2 a = row[ZT::nat(k)], b = (k == 0) ? a : row[ZT::nat(M - k)];
         float2 w = __ldg(p.tw + k);                       // exp(-2 pi i k / NZ)
         float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));   // (a + conj b)/2
         float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));   // (a - conj b)/2
@@ -419,7 +448,7 @@ struct C2RParams {
 
 template <int M>
 __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
-  using P = typename PlanFor<M>::type;
+  using ZT = ZTraits<M>;
   constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = ZTraits<M>::LP;
   extern __shared__ float2 sm[];
   __shared__ double red[2][NT / 32];
@@ -461,8 +490,8 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
         const float2 wc = make_float2(w[i].x, -w[i].y);   // exp(+2 pi i k / NZ)
         const float2 A = make_float2(av.x + bv.x, av.y - bv.y);
         const float2 B = cmul(make_float2(av.x - bv.x, av.y + bv.y), wc);
-        row[k] = make_float2(A.x - B.y, A.y + B.x);        // A + iB
-        if (k != 0 && k != M - k) row[M - k] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
+        row[ZT::idx(k)] = make_float2(A.x - B.y, A.y + B.x);        // A + iB
+        if (k != 0 && k != M - k) row[ZT::idx(M - k)] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
       }
     }
   }
@@ -475,8 +504,7 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
     const int n128 = (int)(nl * p.pitch * 8 / 128);
     for (int i = threadIdx.x; i < n128; i += NT) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + 128LL * i) : "memory");
   }
-  dif_stages_smem<P, 0, P::S - 1, true, LINES, LP, 1, NT>(sm, p.tw, 2);
-  dif_last_resort_smem<P, true, LINES, LP, 1, NT>(sm, p.tw, 2);
+  z_tile_fft<M, true>(sm, p.tw);
   // ---- store x[2n], x[2n+1] = z[n] / N, accumulate sum and sum of squares
   float s1 = 0.f, s2 = 0.f;
   const float rnorm = __frcp_rn(p.norm);
@@ -486,7 +514,7 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
       float2* dst = out2 + (line0 + line) * M;
 #pragma unroll 8
       for (int n = threadIdx.x & 31; n < M; n += 32) {
-        float2 z = sm[line * LP + n];
+        float2 z = sm[line * LP + ZT::nat(n)];
         z.x = fdiv_fast(z.x, p.norm, rnorm);
         z.y = fdiv_fast(z.y, p.norm, rnorm);
         __stcs(dst + n, z);            // written once, read much later: streaming store

@@ -327,7 +327,18 @@ SMK_PLAN(512, 32, 16)
 #else
 SMK_PLAN(512, 8, 8, 8)
 #endif
+// 768 (the z pass, NZ = 1536): SMK_PLAN_768=2 selects 32.24, run by the z kernels without the re-sorting last stage
+// (outputs stay in digit-reversed positions of a padded line and are read back permuted, smk_boxes.cu ZTraits).
+// Measured on B200 (tools/z_sweep.sh): parity green, but c2r z 0.790 -> 0.827 ms -- two shared-memory round trips fewer
+// do not pay for the half-idle second round of the radix-32 stage (384 butterflies on 256 threads) -- so 16.16.3 stays.
+#ifndef SMK_PLAN_768
+#define SMK_PLAN_768 3
+#endif
+#if SMK_PLAN_768 == 2
+SMK_PLAN(768, 32, 24)
+#else
 SMK_PLAN(768, 16, 16, 3)
+#endif
 #if SMK_PLAN_1024 == 2
 SMK_PLAN(1024, 32, 32)
 #else

@@ -84,6 +84,8 @@ static double check_plan(int twmul) {
   double err = 0, nrm = 0;
   bool perm_ok = true;
   for (int p = 0; p < N; ++p) perm_ok = perm_ok && P::pos(P::nat(p)) == p;
+  if (P::S == 2)   // closed form the z kernels use to read a two-stage plan's outputs without a re-sort (ZTraits::nat)
+    for (int k = 0; k < N; ++k) perm_ok = perm_ok && P::pos(k) == (k % P::radix(0)) * P::radix(1) + k / P::radix(0);
   for (int p = 0; p < N; p += step) {
     const int k = P::nat(p);
     double yr = 0, yi = 0;

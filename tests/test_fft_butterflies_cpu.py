@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
-@pytest.mark.parametrize("defines", [(), ("-DSMK_PLAN_512=3", "-DSMK_PLAN_1024=3", "-DSMK_PLAN_2560=3")])
+@pytest.mark.parametrize("defines", [(), ("-DSMK_PLAN_512=3", "-DSMK_PLAN_1024=3", "-DSMK_PLAN_2560=3", "-DSMK_PLAN_768=2")])
 def test_butterflies_and_plans_against_naive_dft(tmp_path, defines):
     if not (os.path.isfile(NVCC) or shutil.which("nvcc")):
         pytest.skip("nvcc not available")
@@ -23,5 +23,6 @@ def test_butterflies_and_plans_against_naive_dft(tmp_path, defines):
     assert "worst plan" in r.stdout
     if defines:         # the three-stage fall-backs of 512 / 1024 and the three-stage 2560 variant
         assert "plan 512 (3 stages, first radix 8)" in r.stdout and "plan 2560 (3 stages, first radix 32)" in r.stdout
+        assert "plan 768 (2 stages, first radix 32)" in r.stdout
     else:
         assert "plan 512 (2 stages, first radix 32)" in r.stdout and "plan 1024 (2 stages, first radix 32)" in r.stdout
