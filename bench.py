@@ -343,6 +343,10 @@ def run_gpu(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                 "passes_ms": per, "passes_gbs": {k: (alg[k] / (per[k] * 1e-3) / 1e9 if per[k] else None) for k in per},
                 "chunk_gbs": (332.0 * cells / world) / (t_box * 1e-3) / 1e9}
+    if world > 1:
+        roofline["note"] = ("N > 1: the x pass runs on a second stream against the y / z passes of the previous product, "
+                            "so the per-pass intervals overlap and each is inflated by the other stream's kernels; the "
+                            "single-GPU line carries the per-kernel roofline")
 
     if rank == 0:
         cpu = None
