@@ -78,7 +78,6 @@ def main():
     bs.dgrowth0 = float(dd[0])
     boxkfile = outDir + "/boxk.npy"
     boxk_exist = os.path.isfile(boxkfile)
-    p0_applied = False
     t0 = time.time()
     if boxk_exist:                                                             # resume, make_boxes.py:209-228
         print("{} already exists ! Reading boxk.npy file to compute density and velocity boxes...".format(boxkfile))
@@ -87,7 +86,16 @@ def main():
             seed = int(np.load(outDir + "/seed_boxk.npy"))
         except Exception:
             print("WARNING: didn't find {}/seed_boxk.npy".format(outDir))
-        p0_applied = a.std() > 70 * NX
+        sigma_k = a.std()
+        if sigma_k > 70 * NX:          # boxk.npy already holds boxk*P0 (make_boxes.py:218-226): undo and save, then go on
+            print("Sigma of boxk is {} > 70*{}:".format(sigma_k, NX))
+            print("dividing boxk by P0(k) and saving...")
+            with np.errstate(divide="ignore", invalid="ignore"):
+                a /= fitsio.read(Pfilename, ext="P0")
+            a[0, 0, 0] = 0j
+            np.save(boxkfile, a)
+        else:
+            print("Sigma of boxk is {} < 70*{}".format(sigma_k, NX))
         boxk = bs.boxk_from_numpy(a)
         del a
     else:
@@ -124,13 +132,10 @@ def main():
         print(boxfile, "written", time.time() - t1, "s")
 
     print("Computing delta boxes...")
-    if p0_applied:
-        print("boxk.npy already holds boxk*P0: lognormal boxes cannot be recomputed from it, skipping them")
-    else:
-        for i in (1, 2, 3):
-            product("boxln_%d" % i, nHDU, "Pln%d" % i)
-        product("box", NX, "P0")                                               # boxk <- boxk*P0 (make_boxes.py:289-291)
-        np.save(boxkfile, bs.boxk_to_numpy(boxk))
+    for i in (1, 2, 3):
+        product("boxln_%d" % i, nHDU, "Pln%d" % i)
+    product("box", NX, "P0")                                                   # boxk <- boxk*P0 (make_boxes.py:289-291)
+    np.save(boxkfile, bs.boxk_to_numpy(boxk))
     if rsd:
         print("Computing eta boxes:")
         for name in ("eta_xx", "eta_yy", "eta_zz", "eta_xy", "eta_xz", "eta_yz"):
