@@ -22,3 +22,14 @@ def golden_small():
 def golden_ref32():
     import numpy as np
     return dict(np.load(os.path.join(GOLDEN, "ref_ref32.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_c1():
+    """BASELINE config 1 (256 x 256 x 1536, the reference's laptop mode) run through the unmodified reference scripts:
+    strided samples of every box, 24 sightlines, merged FLUX (tests/golden/run_reference_shimmed.py c1)."""
+    import numpy as np
+    path = os.path.join(GOLDEN, "ref_c1.npz")
+    if not os.path.isfile(path):
+        pytest.skip("tests/golden/ref_c1.npz not generated")
+    return dict(np.load(path))

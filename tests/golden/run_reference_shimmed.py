@@ -292,6 +292,11 @@ if __name__ == "__main__":
         # 16 x 16 x 96 cells of 35.04 Mpc/h (LZ = 3364 Mpc/h like the nominal box), 4 x-slabs so that
         # some sightlines cross a slab boundary and exercise the piece merge (merge_spectra.py:282-300)
         pipeline("small", 16, 16, 96, 35.04, 4, nq=16, half_angle=2.0, keep_full=True)
+    if which in ("c1",):
+        # BASELINE config 1 (submit_mocks.py --box-size 256: 256 x 256 x 1536 cells of 2.19 Mpc/h, 8 slices,
+        # chunk_parameters(256) window of +-3.17 deg): every box sampled with a stride, 24 sightlines.  Takes ~15 min and
+        # ~10 GB of scratch; not part of "all".
+        pipeline("c1", 256, 256, 1536, 2.19, 8, nq=24, half_angle=3.0, keep_full=False, stride=9973)
     if which in ("ref32", "all"):
         # the reference's own debugging box chunk_parameters(32): 32 x 32 x 1536 cells of 2.19 (4 slabs here)
         pipeline("ref32", 32, 32, 1536, 2.19, 4, nq=12, half_angle=0.3, keep_full=False, stride=97)

@@ -99,12 +99,23 @@ def test_skewers_vs_oracle_no_dla_no_rsd(cuda, golden_small):
 def test_end_to_end_ref32(cuda, golden_ref32):
     """32 x 32 x 1536 reference run: MT19937 noise -> GPU boxes -> GPU skewers -> GPU delta_s (reference noise
     stream) + FGPA -> FLUX of the unmodified merge_spectra.py within 1e-5 absolute."""
+    _end_to_end(cuda, golden_ref32)
+
+
+def test_end_to_end_c1(cuda, golden_c1):
+    """The same chain at BASELINE config 1's full size (256 x 256 x 1536 cells, 8 slices): GPU boxes against the
+    reference's FITS boxes on a strided sample (1e-5 relative L2), GPU skewers against its spectra pieces, GPU FLUX
+    against the unmodified merge_spectra.py within 1e-5 absolute."""
+    _end_to_end(cuda, golden_c1)
+    torch.cuda.empty_cache()
+
+
+def _end_to_end(cuda, g):
     from oracle import boxes as ob
     from oracle import pk_weights
     from oracle import merge as om
     from saclaymocks_b200 import spectra as sp
     from saclaymocks_b200.boxes import BoxSynth, WEIGHT_OF
-    g = golden_ref32
     NX, NY, NZ, dcell = int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"])
     W = pk_weights.weights(NX, NY, NZ, dcell)
     noise = ob.draw_noise(NX, NY, NZ, int(g["seed"]))

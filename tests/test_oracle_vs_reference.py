@@ -121,7 +121,16 @@ def test_merge_matches_merge_spectra_small(golden_small, mode):
 
 def test_ref32_end_to_end(golden_ref32):
     """The reference's own 32 x 32 x 1536 debugging box, seed 42, from noise to FLUX."""
-    g = golden_ref32
+    _end_to_end(golden_ref32)
+
+
+def test_c1_end_to_end(golden_c1):
+    """BASELINE config 1 at full size (256 x 256 x 1536 cells, 8 slices, seed 42): the oracle against the unmodified
+    reference scripts, from noise to FLUX (boxes compared on a strided sample of 1e4 cells each)."""
+    _end_to_end(golden_c1)
+
+
+def _end_to_end(g):
     NX, NY, NZ, dcell, st = int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"]), int(g["stride"])
     W = pk_weights.weights(NX, NY, NZ, dcell)
     for k in ("Pln1", "Pln2", "Pln3", "P0"):
