@@ -181,6 +181,16 @@ int smk_smallscale(smk_ctx* ctx, int nqso, int nfft, int npix, const float* nois
 int smk_fgpa(smk_ctx* ctx, int nqso, int npix, const float* delta_l, const float* delta_s, const float* eta_par,
              const float* growthf, const float* a, const float* b, const float* c, float* flux);
 
+/* ---- skewers with the FGPA fused into the gather's epilogue (make_spectra.py:90-139 followed by util.py:421-433 for
+ * the pixels this slab owns): smk_skewers, then flux = exp(-a exp(b G (delta_l + delta_s + c eta_par))) from the values
+ * still in registers -- the rows delta_l / eta_par are written once and not read back.  delta_s [nqso][npix] comes from
+ * smk_smallscale run BEFORE this call (NULL: no small-scale term); growthf, a, b, c are the [npix] vectors of smk_fgpa.
+ * Pixels past the forest get flux of delta_l = -1e6 (= 1 exactly); pixels of other slabs are left untouched. */
+int smk_skewers_fgpa(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs, double xmin,
+                     double xmax, int rsd, int dla, int nqso, const double* qso_xyzr, const int* npix_forest,
+                     const double* rvec, int npix, float* delta_l, float* eta_par, float* vpar, const float* delta_s,
+                     const float* growthf, const float* a, const float* b, const float* c, float* flux);
+
 /* ---- quasar drawing on device-resident boxes: the cell loop of bin/draw_qso.py for one
  * x-slab -- ptot(z) from the three lognormal boxes (draw_qso.py:228-251), cond1 & cond2 & cond3, the random position
  * inside the cell, (ra, dec) and the redshift-space shift of the quasar redshift (draw_qso.py:394-480).  All pointers

@@ -14,7 +14,7 @@ PRODUCT_ID = {n: i for i, n in enumerate(PRODUCT_NAMES)}
 EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy", "smk_boxk_pitch", "smk_boxk_elems",
            "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
            "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
-           "smk_make_boxes_host", "smk_skewers", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
+           "smk_make_boxes_host", "smk_skewers", "smk_skewers_fgpa", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
            "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate")
 
 
@@ -62,6 +62,7 @@ def lib():
     L.smk_synth_c2r_finish.argtypes = [vp, vp, vp, vp]
     L.smk_make_boxes_host.argtypes = [vp, vp, u64, C.POINTER(vp), d, C.POINTER(vp), C.POINTER(d)]
     L.smk_skewers.argtypes = [vp, C.POINTER(Geom), C.POINTER(vp), i, i, d, d, i, i, i, vp, vp, vp, i, vp, vp, vp]
+    L.smk_skewers_fgpa.argtypes = L.smk_skewers.argtypes + [vp, vp, vp, vp, vp, vp]
     L.smk_smallscale.argtypes = [vp, i, i, i, vp, u64, vp, vp, vp, vp, vp, vp]
     L.smk_fgpa.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.smk_pk_weights.argtypes = [vp, vp, vp, i, vp]

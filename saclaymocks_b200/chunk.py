@@ -54,8 +54,8 @@ class ChunkPipeline(object):
         self.cat = None
         self.footprint = None
         self._qso_setup = None
-        # kernels per step: 3 forward passes + 13 x 3 inverse passes + gather + small-scale + FGPA
-        self.launches_per_step = 3 + 13 * 3 + 3
+        # kernels per step: 3 forward passes + 13 x 3 inverse passes + small-scale + gather (FGPA in its epilogue)
+        self.launches_per_step = 3 + 13 * 3 + (2 if os.environ.get("SMK_FUSED_FGPA", "1") != "0" else 3)
 
     def _connect_exchange(self):
         """Fused exchange set-up: two receive buffers per rank, mapped into every peer through CUDA IPC."""
@@ -253,12 +253,18 @@ class ChunkPipeline(object):
         ix0 = self.rank * self.bs.nxl - self.hlo
         nxs = self.bs.nxl + self.hlo + self.hhi
         L = self.bs.lib
-        _lib.check(L.smk_skewers(self.bs.h, C.byref(cg), fl, ix0, nxs, C.c_double(c["xmin"]), C.c_double(c["xmax"]),
-                                 int(self.rsd), int(self.dla), nq, _ptr(c["xyzr_d"]), _ptr(c["nfor_d"]),
-                                 _ptr(self.eng.rvec), npix, _ptr(dl), _ptr(ep), _ptr(vp)))
+        # small-scale field first, then the gather with the FGPA in its epilogue (delta_l / eta_par are not read back)
         ds = self.fgpa.small_scales(c["nf_merge"], noise=noise, seed=seed, prepared=c["prep"])
-        _lib.check(L.smk_fgpa(self.bs.h, nq, npix, _ptr(dl), _ptr(ds), _ptr(ep), _ptr(self.fgpa.G), _ptr(self.fgpa.a),
-                              _ptr(self.fgpa.b), _ptr(self.fgpa.c), _ptr(F)))
+        args = (self.bs.h, C.byref(cg), fl, ix0, nxs, C.c_double(c["xmin"]), C.c_double(c["xmax"]), int(self.rsd),
+                int(self.dla), nq, _ptr(c["xyzr_d"]), _ptr(c["nfor_d"]), _ptr(self.eng.rvec), npix, _ptr(dl), _ptr(ep),
+                _ptr(vp))
+        if os.environ.get("SMK_FUSED_FGPA", "1") != "0":
+            _lib.check(L.smk_skewers_fgpa(*args, _ptr(ds), _ptr(self.fgpa.G), _ptr(self.fgpa.a), _ptr(self.fgpa.b),
+                                          _ptr(self.fgpa.c), _ptr(F)))
+        else:
+            _lib.check(L.smk_skewers(*args))
+            _lib.check(L.smk_fgpa(self.bs.h, nq, npix, _ptr(dl), _ptr(ds), _ptr(ep), _ptr(self.fgpa.G),
+                                  _ptr(self.fgpa.a), _ptr(self.fgpa.b), _ptr(self.fgpa.c), _ptr(F)))
         self.delta_s = ds
         return self.out
 

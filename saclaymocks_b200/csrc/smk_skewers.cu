@@ -27,6 +27,10 @@ struct SkewerParams {
   float* delta_l;
   float* eta_par;
   float* vpar;
+  // fused FGPA epilogue (smk_skewers_fgpa): flux = exp(-a exp(b G (delta_l + delta_s + c eta_par))), util.py:421-433
+  const float* delta_s;    // [nqso][npix] or null
+  const float *fg_G, *fg_a, *fg_b, *fg_c;   // [npix]
+  float* flux;             // [nqso][npix] or null (no epilogue)
   int pfd;                 // distance (rows of the window) of the L1 row prefetch
   int pf;                  // tuning bits: 1 = L2 prefetch of the next x slab of the window, 2 = L1 prefetch of the next row, 4 = L1 prefetch of the next x slab
 };
@@ -51,6 +55,15 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "=f"(d.x), "=f"(d.y)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
+}
+
+// FGPA of one pixel, the float32 arithmetic of fgpa_kernel (smk_spectra1d.cu) operation for operation
+__device__ __forceinline__ void store_flux(const SkewerParams& p, size_t o, int i, float delta_l, float eta) {
+  float d = delta_l;
+  if (p.delta_s) d += p.delta_s[o];
+  if (p.eta_par && p.fg_c) d += __ldg(p.fg_c + i) * eta;
+  const float tau_over_a = expf(__ldg(p.fg_b + i) * __ldg(p.fg_G + i) * d);   // util.py:427
+  p.flux[o] = expf(-__ldg(p.fg_a + i) * tau_over_a);                          // util.py:428
 }
 
 template <int DMAX, int NF>
@@ -335,6 +348,7 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
       p.delta_l[o] = -1000000.f;
       if (p.eta_par) p.eta_par[o] = 0.f;
       if (p.vpar) p.vpar[o] = 0.f;
+      if (p.flux) store_flux(p, o, i, -1000000.f, 0.f);
       continue;
     }
     ix[k] = (int)((xv + LX / 2) / p.dx);                        // make_spectra.py:47-49
@@ -470,9 +484,12 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
     double xv, yv, zv;
     pixel_xyz<DMAX, P>(p, q, i0 + k, xv, yv, zv);
     const double RR = xv * xv + yv * yv + zv * zv;
-    p.delta_l[o] = d0[k] * inv_sw[k];
-    if (p.eta_par) p.eta_par[o] = NFI >= 7 ? (float)(eta[k] / RR) : 0.f;
+    const float dl = d0[k] * inv_sw[k];
+    const float ep = NFI >= 7 ? (float)(eta[k] / RR) : 0.f;
+    p.delta_l[o] = dl;
+    if (p.eta_par) p.eta_par[o] = ep;
     if (p.vpar) p.vpar[o] = NFI == 10 ? (float)(vel[k] / sqrt(RR)) : 0.f;
+    if (p.flux) store_flux(p, o, i0 + k, dl, ep);
   }
 }
 
@@ -487,7 +504,9 @@ static int launch_multi(const SkewerParams& p, cudaStream_t st) {
   return SMK_OK;
 }
 
-int launch_skewers(const SkewerParams& p, int dmax, double pixel_step, cudaStream_t st) {
+// *fused (if given) tells whether the kernel that ran has the FGPA epilogue (the register-blocked one has)
+int launch_skewers(const SkewerParams& p, int dmax, double pixel_step, cudaStream_t st, bool* fused = nullptr) {
+  if (fused) *fused = false;
   if (p.nqso == 0 || p.npix == 0) return SMK_OK;
   const int NT = 128;
   // register-blocked kernel: valid while P consecutive pixels cannot cross two cell boundaries on any axis
@@ -501,6 +520,7 @@ int launch_skewers(const SkewerParams& p, int dmax, double pixel_step, cudaStrea
   const int PB = (variant == 44 || variant == 42 || variant == 442) ? 4 : variant;
   const bool multi = (dmax == 3) && pixel_step > 0 && (PB - 1) * pixel_step < cell;
   if (multi) {
+    if (fused) *fused = true;
     switch (variant) {
       case 2: return launch_multi<2, 5>(p, st);
       case 3: return launch_multi<3, 4>(p, st);
@@ -526,10 +546,11 @@ int launch_skewers(const SkewerParams& p, int dmax, double pixel_step, cudaStrea
 
 }  // namespace smk
 
-extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs,
-                           double xmin, double xmax, int rsd, int dla, int nqso, const double* qso_xyzr,
-                           const int* npix_forest, const double* rvec, int npix, float* delta_l, float* eta_par,
-                           float* vpar) {
+static int skewers_impl(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs,
+                        double xmin, double xmax, int rsd, int dla, int nqso, const double* qso_xyzr,
+                        const int* npix_forest, const double* rvec, int npix, float* delta_l, float* eta_par,
+                        float* vpar, const float* delta_s, const float* growthf, const float* fa, const float* fb,
+                        const float* fc, float* flux) {
   using namespace smk;
   if (nqso == 0 || npix == 0) return SMK_OK;     // empty catalogue: nothing to do (empty tensors have null pointers)
   if (!g || !fields || !fields[0] || !delta_l || (nqso > 0 && (!qso_xyzr || !npix_forest || !rvec))) {
@@ -553,6 +574,7 @@ extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const f
   p.nqso = nqso; p.npix = npix;
   p.qso = qso_xyzr; p.npix_forest = npix_forest; p.rvec = rvec;
   p.delta_l = delta_l; p.eta_par = eta_par; p.vpar = vpar;
+  p.delta_s = delta_s; p.fg_G = growthf; p.fg_a = fa; p.fg_b = fb; p.fg_c = fc; p.flux = flux;
   { const char* e = getenv("SMK_SKEW_PF"); p.pf = e ? atoi(e) : 2; }
   { const char* e = getenv("SMK_SKEW_PFD"); p.pfd = e ? atoi(e) : 1; if (p.pfd < 1 || p.pfd > 7) p.pfd = 1; }
   // largest step between consecutive pixels of the grid (uniform 0.2 Mpc/h in the reference); decides whether the
@@ -560,5 +582,30 @@ extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const f
   double step = g->pixel_step;
   const char* env = getenv("SMK_SKEWERS_SIMPLE");
   if (env && env[0] == '1') step = 0.0;
-  return launch_skewers(p, g->dmax, step, smk_ctx_stream(ctx));
+  bool fused = false;
+  int rc = launch_skewers(p, g->dmax, step, smk_ctx_stream(ctx), &fused);
+  if (rc != SMK_OK || !flux || fused) return rc;
+  // the one-pixel-per-thread kernel has no epilogue: FGPA as a separate pass over the rows
+  return smk_fgpa(ctx, nqso, npix, delta_l, delta_s, eta_par, growthf, fa, fb, fc, flux);
+}
+
+extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs,
+                           double xmin, double xmax, int rsd, int dla, int nqso, const double* qso_xyzr,
+                           const int* npix_forest, const double* rvec, int npix, float* delta_l, float* eta_par,
+                           float* vpar) {
+  return skewers_impl(ctx, g, fields, ix0, nxs, xmin, xmax, rsd, dla, nqso, qso_xyzr, npix_forest, rvec, npix, delta_l,
+                      eta_par, vpar, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int smk_skewers_fgpa(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs,
+                                double xmin, double xmax, int rsd, int dla, int nqso, const double* qso_xyzr,
+                                const int* npix_forest, const double* rvec, int npix, float* delta_l, float* eta_par,
+                                float* vpar, const float* delta_s, const float* growthf, const float* a, const float* b,
+                                const float* c, float* flux) {
+  if (!flux || !growthf || !a || !b || (rsd && !c)) {
+    smk::set_error("smk_skewers_fgpa: flux and the FGPA parameter vectors are required");
+    return SMK_ERR_ARG;
+  }
+  return skewers_impl(ctx, g, fields, ix0, nxs, xmin, xmax, rsd, dla, nqso, qso_xyzr, npix_forest, rvec, npix, delta_l,
+                      eta_par, vpar, delta_s, growthf, a, b, c, flux);
 }

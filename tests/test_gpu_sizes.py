@@ -172,3 +172,11 @@ def test_run_chunk_resident_chain(cuda):
             assert np.all((f >= 0) & (f <= 1))           # float32 F underflows to 0 in dense absorbers
             checked += int(m.sum())
     assert checked > 1000
+    # the FGPA fused into the gather's epilogue (smk_skewers_fgpa, what step_skewers runs) against the separate pass
+    # (smk_fgpa) over the same rows; pixels of no slab stay untouched in both (NaN after the refill)
+    for t in pipe.out:
+        t.fill_(float("nan"))
+    dl_t, ep_t, vp_t, F_t = pipe.step_skewers(seed=5)
+    F_sep = pipe.fgpa.flux(dl_t, pipe.delta_s, ep_t)
+    assert torch.isfinite(F_t).sum() > 1000 and bool((torch.isfinite(F_t) == torch.isfinite(dl_t)).all())
+    assert float((torch.nan_to_num(F_t, nan=2.0) - torch.nan_to_num(F_sep, nan=2.0)).abs().max()) < 1e-6
