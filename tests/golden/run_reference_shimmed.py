@@ -297,6 +297,10 @@ if __name__ == "__main__":
         # chunk_parameters(256) window of +-3.17 deg): every box sampled with a stride, 24 sightlines.  Takes ~15 min and
         # ~10 GB of scratch; not part of "all".
         pipeline("c1", 256, 256, 1536, 2.19, 8, nq=24, half_angle=3.0, keep_full=False, stride=9973)
+    if which in ("c2",):
+        # BASELINE config 2, the bench workload (512 x 512 x 1536 cells of 2.19 Mpc/h, 8 slices, window of +-6.4 deg):
+        # every box sampled with a stride, 32 sightlines.  ~25 GB of scratch, ~30 min; not part of "all".
+        pipeline("c2", 512, 512, 1536, 2.19, 8, nq=32, half_angle=6.0, keep_full=False, stride=39989)
     if which in ("ref32", "all"):
         # the reference's own debugging box chunk_parameters(32): 32 x 32 x 1536 cells of 2.19 (4 slabs here)
         pipeline("ref32", 32, 32, 1536, 2.19, 4, nq=12, half_angle=0.3, keep_full=False, stride=97)

@@ -110,6 +110,13 @@ def test_end_to_end_c1(cuda, golden_c1):
     torch.cuda.empty_cache()
 
 
+def test_end_to_end_c2(cuda, golden_c2):
+    """The same chain at the bench workload's size (BASELINE config 2, 512 x 512 x 1536) against the unmodified
+    reference's files; the oracle's weight tables and MT19937 noise take minutes on the host: SMK_SLOW_TESTS=1."""
+    _end_to_end(cuda, golden_c2)
+    torch.cuda.empty_cache()
+
+
 def _end_to_end(cuda, g):
     from oracle import boxes as ob
     from oracle import pk_weights

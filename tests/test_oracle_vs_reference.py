@@ -130,6 +130,11 @@ def test_c1_end_to_end(golden_c1):
     _end_to_end(golden_c1)
 
 
+def test_c2_end_to_end(golden_c2):
+    """BASELINE config 2, the bench workload, at full size (512 x 512 x 1536): minutes of CPU work, SMK_SLOW_TESTS=1."""
+    _end_to_end(golden_c2)
+
+
 def _end_to_end(g):
     NX, NY, NZ, dcell, st = int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"]), int(g["stride"])
     W = pk_weights.weights(NX, NY, NZ, dcell)
