@@ -124,11 +124,20 @@ def _end_to_end(cuda, g):
     from saclaymocks_b200 import spectra as sp
     from saclaymocks_b200.boxes import BoxSynth, WEIGHT_OF
     NX, NY, NZ, dcell = int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"])
-    W = pk_weights.weights(NX, NY, NZ, dcell)
     noise = ob.draw_noise(NX, NY, NZ, int(g["seed"]))
     bs = BoxSynth(NX, NY, NZ, dcell, device=cuda)
     boxk = bs.draw_grf_boxk(noise=torch.as_tensor(noise, device=cuda))
-    Wd = {k: bs.upload_weights(v) for k, v in W.items()}
+    if NX * NY * NZ > 2e8:      # config 2: the host spline evaluation of 8e8 table entries takes minutes; the GPU tables
+        Wd = {k: bs.weight_table(k) for k in ("Pln1", "Pln2", "Pln3", "P0")}     # are bit-equal to > 99.9 %, 1 ulp else
+        st = int(g["stride"])
+        for k, t in Wd.items():
+            got = t.cpu().numpy().ravel()[::st]
+            ref = g["W_" + k]
+            assert (got == ref).mean() > 0.999, k
+            assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)) < 2.5e-7, k     # W(k = 0) is exactly 0
+    else:
+        W = pk_weights.weights(NX, NY, NZ, dcell)
+        Wd = {k: bs.upload_weights(v) for k, v in W.items()}
     bs.synth(boxk, "box", wtable=Wd["P0"])[0]
     fields = {}
     for name in sp.FIELDS:
