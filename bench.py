@@ -212,7 +212,22 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def quiet_stdout():
+    """Reserve stdout for the ONE JSON line: whatever a library writes to file descriptor 1 meanwhile (NCCL prints its
+    version banner there when NCCL_DEBUG is set) is sent to stderr.  Returns the descriptor of the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def emit(real_fd, text):
+    sys.stdout.flush()
+    os.write(real_fd, (text + "\n").encode())
+
+
 def run_gpu(args):
+    real_stdout = quiet_stdout()
     import torch
     import torch.distributed as dist
     from saclaymocks_b200 import spectra as sp
@@ -374,7 +389,7 @@ def run_gpu(args):
                 "nqso_drawn_rank0": int(nq_drawn),
                 "wall_s": wall, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": pipe.launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(real_stdout, json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -154,3 +154,14 @@ def test_chunk_parameters_match_the_reference_table():
     assert chunks.chunk_window(512, 6) == (202.8, 6.4, 12.8, 6.4)
     with pytest.raises(ValueError):
         chunks.chunk_parameters(100)
+
+
+def test_bench_keeps_stdout_for_the_json_line():
+    """bench.quiet_stdout / emit: anything written to fd 1 between the two (python prints, a child process, NCCL's
+    banner) lands on stderr; stdout carries exactly the emitted line."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; fd = bench.quiet_stdout(); print('junk'); "
+            "os.system('echo junk2'); bench.emit(fd, '{\"ok\": 1}')" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == '{"ok": 1}\n'
+    assert "junk" in r.stderr and "junk2" in r.stderr
