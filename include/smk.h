@@ -58,6 +58,10 @@ int smk_version(void);
  * dcell = cell size in Mpc/h (make_boxes.py -pixel).  stream = cudaStream_t (NULL = default stream).
  * rank/nranks describe the slab decomposition; nranks > 1 requires nx % nranks == 0 and ny % nranks == 0. */
 int smk_ctx_create(smk_ctx** ctx, int nx, int ny, int nz, double dcell, int rank, int nranks, void* stream);
+/* A context without an FFT plan: it carries a stream (and the library's small scratch) for the entry points that do not
+ * transform boxes -- smk_skewers, smk_skewers_fgpa, smk_smallscale, smk_fgpa, smk_p1d, smk_draw_qso.  (The per-quasar
+ * loop of make_spectra.py / merge_spectra.py has no plan either.)  The box entry points refuse it with SMK_ERR_ARG. */
+int smk_ctx_create_light(smk_ctx** ctx, void* stream);
 int smk_ctx_destroy(smk_ctx* ctx);
 int smk_boxk_pitch(const smk_ctx* ctx);           /* complex elements per kz row */
 size_t smk_boxk_elems(const smk_ctx* ctx);        /* complex elements of this rank's boxk */

@@ -18,6 +18,17 @@ def draw_noise(NX, NY, NZ, seed):
     return box
 
 
+def draw_noise_planes(NX, NY, NZ, seed):
+    """The same stream as draw_noise, returned plane-major [NZ][NX][NY] (contiguous writes: 14 s instead of a minute
+    at 512 x 512 x 1536); draw_noise(...)[x, y, z] == draw_noise_planes(...)[z, x, y].  The GPU tests upload this
+    and permute on the device."""
+    np.random.seed(seed)
+    box = np.empty((NZ, NX, NY), dtype=np.float32)
+    for iz in range(NZ):
+        box[iz] = np.random.normal(size=[NX, NY])
+    return box
+
+
 def forward(box, workers=1):
     """make_boxes.py:52-54: unnormalised r2c over all three axes, complex64."""
     boxk = sfft.rfftn(box, axes=(0, 1, 2), workers=workers)

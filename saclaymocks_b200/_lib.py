@@ -15,7 +15,7 @@ EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy",
            "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
            "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
            "smk_make_boxes_host", "smk_skewers", "smk_skewers_fgpa", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
-           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate")
+           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light")
 
 
 class SmkError(RuntimeError):
@@ -43,6 +43,7 @@ def lib():
     L.smk_last_error.restype = C.c_char_p
     L.smk_version.restype = i
     L.smk_ctx_create.argtypes = [C.POINTER(vp), i, i, i, d, i, i, vp]
+    L.smk_ctx_create_light.argtypes = [C.POINTER(vp), vp]
     L.smk_ctx_destroy.argtypes = [vp]
     L.smk_boxk_pitch.argtypes = [vp]
     L.smk_boxk_elems.argtypes = [vp]
@@ -82,6 +83,36 @@ def lib():
             getattr(L, name).restype = i
     _lib = L
     return L
+
+
+class StreamCtx(object):
+    """A light library context (smk_ctx_create_light) that follows torch's current stream: `handle()` re-binds it to
+    the stream that is current on `device` at the time of the call, so kernels are ordered like any other torch work
+    (passing NULL instead would put them on the legacy default stream)."""
+
+    def __init__(self, device):
+        import torch
+        self._torch = torch
+        self.device = device
+        self.lib = lib()
+        h = C.c_void_p()
+        check(self.lib.smk_ctx_create_light(C.byref(h), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        self.h = h
+
+    def handle(self):
+        self.lib.smk_set_stream(self.h, C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream))
+        return self.h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.smk_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def check(rc):

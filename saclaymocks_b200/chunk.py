@@ -102,7 +102,9 @@ class ChunkPipeline(object):
         self.cat["nfor_d"] = torch.as_tensor(self.cat["nfor"], device=self.device)
         self.cat["nf_merge"] = self.fgpa.forest_count(self.cat["z"])
         self.cat["prep"] = self.fgpa.prepare(self.cat["nf_merge"], self.cat["ids"])
-        self.out = tuple(torch.empty((nq, npix), dtype=torch.float32, device=self.device) for _ in range(4))
+        # rows are written only at the pixels this slab owns (smk_skewers: xmin < X <= xmax); everything else keeps this
+        # NaN, which is what merging the slabs' pieces selects on (gather_rows; bin/make_spectra.py relies on the same mask)
+        self.out = tuple(torch.full((nq, npix), float("nan"), dtype=torch.float32, device=self.device) for _ in range(4))
         # pixels this rank owns: xmin < X <= xmax and inside the forest (for the pixel-rate metric)
         own = 0
         for i0 in range(0, nq, 4096):
@@ -170,26 +172,30 @@ class ChunkPipeline(object):
             X = self._xstream
             X.wait_stream(main)                         # boxk (forward transform) is ready
             ev_yz = [None, None]
-            for q, name in enumerate(products):
-                slot = q & 1
-                pid = _lib.PRODUCT_ID[name]
-                wt = self.W[WEIGHT_OF[name]] if name in WEIGHT_OF else None
-                with torch.cuda.stream(X):
-                    L.smk_set_stream(bs.h, C.c_void_p(X.cuda_stream))
-                    # x(q) overwrites buffer `slot` on the peers: they finished reading it (yz(q-2)) before they
-                    # entered barrier(q-1), which precedes x(q) on this stream
-                    _lib.check(L.smk_synth_c2r_local_p2p(bs.h, _ptr(self.boxk), pid, _ptr(wt), 1,
-                                                         C.c_double(bs.dgrowth0), slot))
-                    if ev_yz[slot ^ 1] is not None:
-                        X.wait_event(ev_yz[slot ^ 1])   # yz(q-1) done before this rank enters barrier(q)
-                    self._stream_barrier()
-                    ev_bar = torch.cuda.Event()
-                    ev_bar.record(X)
+            try:
+                for q, name in enumerate(products):
+                    slot = q & 1
+                    pid = _lib.PRODUCT_ID[name]
+                    wt = self.W[WEIGHT_OF[name]] if name in WEIGHT_OF else None
+                    with torch.cuda.stream(X):
+                        L.smk_set_stream(bs.h, C.c_void_p(X.cuda_stream))
+                        # x(q) overwrites buffer `slot` on the peers: they finished reading it (yz(q-2)) before they
+                        # entered barrier(q-1), which precedes x(q) on this stream
+                        _lib.check(L.smk_synth_c2r_local_p2p(bs.h, _ptr(self.boxk), pid, _ptr(wt), 1,
+                                                             C.c_double(bs.dgrowth0), slot))
+                        if ev_yz[slot ^ 1] is not None:
+                            X.wait_event(ev_yz[slot ^ 1])   # yz(q-1) done before this rank enters barrier(q)
+                        self._stream_barrier()
+                        ev_bar = torch.cuda.Event()
+                        ev_bar.record(X)
+                    L.smk_set_stream(bs.h, C.c_void_p(main.cuda_stream))
+                    main.wait_event(ev_bar)
+                    _lib.check(L.smk_synth_c2r_finish_p2p(bs.h, slot, _ptr(self.interior(name)), _ptr(self.stats[pid])))
+                    ev_yz[slot] = torch.cuda.Event()
+                    ev_yz[slot].record(main)
+            finally:                                   # whatever happened, the ctx goes back to the caller's stream
                 L.smk_set_stream(bs.h, C.c_void_p(main.cuda_stream))
-                main.wait_event(ev_bar)
-                _lib.check(L.smk_synth_c2r_finish_p2p(bs.h, slot, _ptr(self.interior(name)), _ptr(self.stats[pid])))
-                ev_yz[slot] = torch.cuda.Event()
-                ev_yz[slot].record(main)
+                main.wait_stream(X)
             return
         pending = None            # (work, slot, name)
         for i, name in enumerate(products):

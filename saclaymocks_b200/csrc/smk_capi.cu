@@ -212,6 +212,27 @@ static int chain_forward_zy(smk_ctx* c, const float* box_slab, uint64_t seed, fl
   return rc;
 }
 
+static int ctx_allocate(smk_ctx* c) {
+  int rc;
+  if ((rc = make_twiddles(c->nx, &c->tw_x, &c->bytes))) return rc;
+  if ((rc = make_twiddles(c->ny, &c->tw_y, &c->bytes))) return rc;
+  if ((rc = make_twiddles(c->nz, &c->tw_z, &c->bytes))) return rc;
+  if ((rc = make_ktable(c->nx, false, c->dcell, &c->kx, &c->bytes))) return rc;
+  if ((rc = make_ktable(c->ny, false, c->dcell, &c->ky, &c->bytes))) return rc;
+  if ((rc = make_ktable(c->nz, true, c->dcell, &c->kz, &c->bytes))) return rc;
+  size_t wbytes = (size_t)c->nxl * c->ny * c->pitch * sizeof(float2);
+  SMK_CUDA_OK(cudaMalloc(&c->work, wbytes));
+  c->bytes += wbytes;
+  SMK_CUDA_OK(cudaMalloc(&c->stats, 2 * SMK_NPRODUCTS * sizeof(double)));
+  return chain_setup(c);
+}
+
+// entry points that need the FFT plan refuse a light context (smk_ctx_create_light: stream + scratch only)
+#define SMK_NEED_PLAN(c, what)                                                                  \
+  do {                                                                                          \
+    if (!(c) || (c)->nx <= 0) { set_error(what ": needs a context made by smk_ctx_create"); return SMK_ERR_ARG; } \
+  } while (0)
+
 extern "C" {
 
 const char* smk_last_error(void) { return g_err.c_str(); }
@@ -237,18 +258,23 @@ int smk_ctx_create(smk_ctx** out, int nx, int ny, int nz, double dcell, int rank
   c->rank = rank; c->nranks = nranks; c->nxl = nx / nranks; c->nyl = ny / nranks;
   c->dcell = dcell;
   c->stream = (cudaStream_t)stream;
-  int rc;
-  if ((rc = make_twiddles(nx, &c->tw_x, &c->bytes))) return rc;
-  if ((rc = make_twiddles(ny, &c->tw_y, &c->bytes))) return rc;
-  if ((rc = make_twiddles(nz, &c->tw_z, &c->bytes))) return rc;
-  if ((rc = make_ktable(nx, false, dcell, &c->kx, &c->bytes))) return rc;
-  if ((rc = make_ktable(ny, false, dcell, &c->ky, &c->bytes))) return rc;
-  if ((rc = make_ktable(nz, true, dcell, &c->kz, &c->bytes))) return rc;
-  size_t wbytes = (size_t)c->nxl * ny * c->pitch * sizeof(float2);
-  SMK_CUDA_OK(cudaMalloc(&c->work, wbytes));
-  c->bytes += wbytes;
-  SMK_CUDA_OK(cudaMalloc(&c->stats, 2 * SMK_NPRODUCTS * sizeof(double)));
-  if ((rc = chain_setup(c))) return rc;
+  int rc = ctx_allocate(c);
+  if (rc) {                  // nothing of a half-built context survives a failure (smk_ctx_destroy frees what exists)
+    const std::string why = g_err;
+    smk_ctx_destroy(c);
+    set_error(why);
+    return rc;
+  }
+  *out = c;
+  return SMK_OK;
+}
+
+int smk_ctx_create_light(smk_ctx** out, void* stream) {
+  if (!out) { set_error("smk_ctx_create_light: null argument"); return SMK_ERR_ARG; }
+  smk_ctx* c = new smk_ctx();
+  c->nx = c->ny = c->nz = c->nzh = c->pitch = c->nxl = c->nyl = 0;
+  c->rank = 0; c->nranks = 1; c->dcell = 0.0;
+  c->stream = (cudaStream_t)stream;
   *out = c;
   return SMK_OK;
 }
@@ -288,6 +314,7 @@ int smk_sync(smk_ctx* c) {
 }
 
 int smk_pk_weights(smk_ctx* c, const double* breaks, const double* coefs, int nint, float* wtable) {
+  SMK_NEED_PLAN(c, "smk_pk_weights");
   if (!breaks || !coefs || nint < 1 || !wtable) { set_error("smk_pk_weights: bad argument"); return SMK_ERR_ARG; }
   PkParams p{breaks, coefs, nint, c->kx, c->ky, c->kz, c->nx, c->nyl, c->nzh, c->rank * c->nyl,
              (float)(c->dcell * c->dcell * c->dcell), wtable};
@@ -295,6 +322,7 @@ int smk_pk_weights(smk_ctx* c, const double* breaks, const double* coefs, int ni
 }
 
 int smk_pk_estimate(smk_ctx* c, const void* boxk, int nbins, double kmin, double kmax, double* sums) {
+  SMK_NEED_PLAN(c, "smk_pk_estimate");
   if (!boxk || !sums) { set_error("smk_pk_estimate: null argument"); return SMK_ERR_ARG; }
   return launch_pk_estimate((const float2*)boxk, c->kx, c->ky, c->kz, c->nx, c->nyl, c->nzh, c->pitch, c->rank * c->nyl,
                             c->nz, nbins, kmin, kmax, sums, c->stream);
@@ -322,12 +350,14 @@ int smk_timing_collect(smk_ctx* c, double ms_sum[SMK_NPASSES], int count[SMK_NPA
 }
 
 int smk_noise_philox(smk_ctx* c, uint64_t seed, float* box_slab) {
+  SMK_NEED_PLAN(c, "smk_noise_philox");
   long long ncells = (long long)c->nxl * c->ny * c->nz;
   return launch_philox_fill(box_slab, ncells, seed, (long long)c->rank * ncells, c->stream);
 }
 
 // ---- forward
 int smk_fft_r2c_local(smk_ctx* c, const float* box_slab, uint64_t seed, void* sendbuf) {
+  SMK_NEED_PLAN(c, "smk_fft_r2c_local");
   long long nlines = (long long)c->nxl * c->ny;
   long long cell0 = (long long)c->rank * nlines * c->nz;
   float2* tmp = (c->nranks == 1) ? (float2*)sendbuf : c->work;
@@ -350,6 +380,7 @@ int smk_fft_r2c_local(smk_ctx* c, const float* box_slab, uint64_t seed, void* se
 }
 
 int smk_fft_r2c_finish(smk_ctx* c, const void* recvbuf, void* boxk) {
+  SMK_NEED_PLAN(c, "smk_fft_r2c_finish");
   // x pass on [nx][nyl][pitch]: outer = local y
   PassAddr a{(long long)c->pitch, 0, (long long)c->nyl * c->pitch, c->nx};
   MulArgs m{};
@@ -370,6 +401,7 @@ int smk_fft_r2c(smk_ctx* c, const float* box_slab, uint64_t seed, void* boxk) {
 // ---- inverse
 int smk_synth_c2r_local(smk_ctx* c, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
                         void* sendbuf) {
+  SMK_NEED_PLAN(c, "smk_synth_c2r_local");
   if (product < 0 || product >= SMK_NPRODUCTS) { set_error("bad product id"); return SMK_ERR_ARG; }
   MulArgs m{};
   int mode;
@@ -400,6 +432,7 @@ int smk_synth_c2r_local(smk_ctx* c, void* boxk, int product, const float* wtable
 
 // ---- fused exchange: the inverse x pass stores straight into the peers' receive buffers over NVLink
 int smk_exchange_create(smk_ctx* c, int nbuf) {
+  SMK_NEED_PLAN(c, "smk_exchange_create");
   if (nbuf < 1 || nbuf > 4 || c->nxbuf) { set_error("smk_exchange_create: nbuf must be 1..4, once per ctx"); return SMK_ERR_ARG; }
   size_t bytes = smk_boxk_elems(c) * sizeof(float2);
   for (int b = 0; b < nbuf; ++b) {
@@ -439,6 +472,7 @@ void* smk_exchange_ptr(smk_ctx* c, int buf) { return (buf >= 0 && buf < c->nxbuf
 
 int smk_synth_c2r_local_p2p(smk_ctx* c, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
                             int buf) {
+  SMK_NEED_PLAN(c, "smk_synth_c2r_local_p2p");
   if (buf < 0 || buf >= c->nxbuf || !c->xconnected[buf]) { set_error("smk_synth_c2r_local_p2p: exchange buffer not connected"); return SMK_ERR_ARG; }
   if (c->nranks < 2 || c->nxl < 2) { set_error("smk_synth_c2r_local_p2p: needs >= 2 ranks and >= 2 planes per rank"); return SMK_ERR_ARG; }
   if (product < 0 || product >= SMK_NPRODUCTS) { set_error("bad product id"); return SMK_ERR_ARG; }
@@ -479,6 +513,7 @@ int smk_synth_c2r_local_p2p(smk_ctx* c, void* boxk, int product, const float* wt
 }
 
 int smk_synth_c2r_finish_p2p(smk_ctx* c, int buf, float* out_slab, double* stats) {
+  SMK_NEED_PLAN(c, "smk_synth_c2r_finish_p2p");
   if (buf < 0 || buf >= c->nxbuf) { set_error("smk_synth_c2r_finish_p2p: bad buffer index"); return SMK_ERR_ARG; }
   // y pass reading the tiled receive layout [src][kz tile][y_l][x_l][LX]: y = src*nyl + y_l
   const long long chunk = (long long)c->nxl * c->nyl * c->pitch;
@@ -501,6 +536,7 @@ int smk_synth_c2r_finish_p2p(smk_ctx* c, int buf, float* out_slab, double* stats
 }
 
 int smk_synth_c2r_finish(smk_ctx* c, void* recvbuf, float* out_slab, double* stats) {
+  SMK_NEED_PLAN(c, "smk_synth_c2r_finish");
   // y pass: input [src][xl][yl][z] (y = src*nyl + yl), output [xl][ny][pitch]
   PassAddr ain{(long long)c->nyl * c->pitch, (long long)c->nxl * c->nyl * c->pitch, (long long)c->pitch, c->nyl};
   if (c->yz_group > 0) return chain_inverse_yz(c, (const float2*)recvbuf, ain, out_slab, stats);
@@ -528,13 +564,31 @@ int smk_synth_c2r(smk_ctx* c, void* boxk, int product, const float* wtable, int 
 
 int smk_make_boxes_host(smk_ctx* c, const float* noise_host, uint64_t seed, const float* const wtables_host[4],
                         double dgrowth0, float* const out_host[SMK_NPRODUCTS], double sigma_out[SMK_NPRODUCTS]) {
+  SMK_NEED_PLAN(c, "smk_make_boxes_host");
   if (c->nranks != 1) { set_error("smk_make_boxes_host: single rank only"); return SMK_ERR_ARG; }
   size_t ncell = (size_t)c->nx * c->ny * c->nz, nk = smk_boxk_elems(c), nw = (size_t)c->nx * c->ny * c->nzh;
-  float2* boxk = nullptr;
-  float* wt = nullptr;
-  float* box[2] = {nullptr, nullptr};
-  cudaStream_t copy_stream;
-  cudaEvent_t done[2], copied[2];
+  // every resource of the call lives in this guard: any early return (SMK_CUDA_OK, argument errors) releases all of it
+  struct Guard {
+    float2* boxk = nullptr;
+    float* wt = nullptr;
+    float* box[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    ~Guard() {
+      cudaFree(boxk); cudaFree(wt); cudaFree(box[0]); cudaFree(box[1]);
+      if (copy_stream) cudaStreamDestroy(copy_stream);
+      for (int i = 0; i < 2; ++i) {
+        if (done[i]) cudaEventDestroy(done[i]);
+        if (copied[i]) cudaEventDestroy(copied[i]);
+      }
+    }
+  } g;
+  float2*& boxk = g.boxk;
+  float*& wt = g.wt;
+  float** box = g.box;
+  cudaStream_t& copy_stream = g.copy_stream;
+  cudaEvent_t* done = g.done;
+  cudaEvent_t* copied = g.copied;
   SMK_CUDA_OK(cudaMalloc(&boxk, nk * sizeof(float2)));
   SMK_CUDA_OK(cudaMalloc(&wt, nw * sizeof(float)));
   SMK_CUDA_OK(cudaMalloc(&box[0], ncell * sizeof(float)));
@@ -574,14 +628,12 @@ int smk_make_boxes_host(smk_ctx* c, const float* noise_host, uint64_t seed, cons
     ++nb;
   }
   double hstats[2 * SMK_NPRODUCTS];
+  // drain both streams before the guard frees anything, whatever happened above
   cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(copy_stream);
-  cudaMemcpy(hstats, c->stats, sizeof(hstats), cudaMemcpyDeviceToHost);
-  cudaFree(boxk); cudaFree(wt); cudaFree(box[0]); cudaFree(box[1]);
-  cudaStreamDestroy(copy_stream);
-  for (int i = 0; i < 2; ++i) { cudaEventDestroy(done[i]); cudaEventDestroy(copied[i]); }
   if (rc) return rc;
   SMK_CUDA_OK(e1);
   SMK_CUDA_OK(e2);
+  SMK_CUDA_OK(cudaMemcpy(hstats, c->stats, sizeof(hstats), cudaMemcpyDeviceToHost));
   for (int p = 0; p < SMK_NPRODUCTS; ++p) {
     double s1 = hstats[2 * p], s2 = hstats[2 * p + 1], n = (double)ncell;
     double var = s2 / n - (s1 / n) * (s1 / n);

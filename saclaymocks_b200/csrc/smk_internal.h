@@ -102,3 +102,5 @@ bool z_size_supported(int nz);
 cudaStream_t smk_ctx_stream(const smk_ctx* ctx);
 // persistent device scratch of at least `bytes` owned by the context (grown on demand; nullptr + error set on failure)
 void* smk_ctx_scratch(smk_ctx* ctx, size_t bytes);
+// device twiddle table W_nfft[k] = exp(-2 pi i k / nfft) of the 1-D transforms, cached per (device, nfft)
+int smk_tw1d(int nfft, const float2** out);

@@ -45,8 +45,10 @@ __device__ __forceinline__ double diffmod(double a, double b, double c) {       
 }
 
 // 53-bit uniform in [0,1) from Philox: same construction as NumPy's random_sample ((a >> 5) * 2^26 + (b >> 6)) / 2^53
+// Counter word 3 carries a domain tag: the white noise of the boxes (smk_philox.cuh) uses tag 0, the cond1 variates
+// 0x51 and these streams 0x52, so that no two consumers of the same seed ever share a Philox block.
 __device__ __forceinline__ void philox_uniform2(uint64_t seed, uint64_t ctr, uint32_t stream, double& u0, double& u1) {
-  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), stream, 0u};
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), stream, 0x52u};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   u0 = ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6)) / 9007199254740992.0;
   u1 = ((double)(c[2] >> 5) * 67108864.0 + (double)(c[3] >> 6)) / 9007199254740992.0;
@@ -115,6 +117,16 @@ __device__ __noinline__ void finish_cell(const smk_qso_params& p, size_t idx, in
   }
 }
 
+// cond1 variate of cell (ix, iy, mz) in Philox mode: one Philox block per four consecutive z cells of a column, a
+// 32-bit draw scaled in float32 -- the SAME variate in the exact and the production kernel, so that their selections
+// differ only where the production kernel's float32 ptot rounds across the variate (tests/test_gpu_qso.py)
+__device__ __forceinline__ void cond1_block(const smk_qso_params& p, int ix, int iy, int iz4, uint32_t (&c)[4]) {
+  const uint64_t col = (uint64_t)(p.ix0 + ix) * p.ny + iy;
+  c[0] = (uint32_t)col; c[1] = (uint32_t)(col >> 32); c[2] = (uint32_t)iz4; c[3] = 0x51u;
+  philox4x32_10(c, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+}
+__device__ __forceinline__ float cond1_uniform(uint32_t w) { return (float)w * 2.3283064365386963e-10f; }
+
 // uniforms of a cond1 survivor in Philox mode: the reference shares one x offset per (plane, ix) and one y offset per
 // (plane, iy), so those are keyed on the row; u2 and uz on the global cell
 __device__ __forceinline__ void survivor_uniforms(const smk_qso_params& p, int ix, int iy, int mz, double& u2, double& ux,
@@ -151,8 +163,9 @@ __global__ void __launch_bounds__(256) draw_qso_kernel(const smk_qso_params p, i
     if (p.u1) {
       u1 = p.u1[pl];
     } else {
-      double d;
-      philox_uniform2(p.seed, ((uint64_t)(p.ix0 + ix) * p.ny + iy) * p.nz + mz, 0u, u1, d);
+      uint32_t c[4];
+      cond1_block(p, ix, iy, mz >> 2, c);
+      u1 = (double)cond1_uniform(c[mz & 3]);
     }
     if (!(u1 < p.norm * ptot)) continue;                               // cond1 (:427)
     atomicAdd(counters + 1, 1);                                        // "QSOs in the full box" (:430)
@@ -231,9 +244,8 @@ __global__ void __launch_bounds__(256, 3) draw_qso_fast_kernel(const smk_qso_par
     const float4 g1 = __ldcs(b1 + q), g2 = __ldcs(b2 + q), g3 = __ldcs(b3 + q);
     const float xa = (float)__ldg(p.x_axis + ix), ya = (float)__ldg(p.y_axis + iy);
     const float xy2 = fmaf(xa, xa, ya * ya);
-    uint32_t c[4] = {(uint32_t)((uint64_t)(p.ix0 + ix) * p.ny + iy), (uint32_t)(((uint64_t)(p.ix0 + ix) * p.ny + iy) >> 32),
-                     (uint32_t)iz4, 0x51u};
-    philox4x32_10(c, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    uint32_t c[4];
+    cond1_block(p, ix, iy, iz4, c);
     const float gg1[4] = {g1.x, g1.y, g1.z, g1.w}, gg2[4] = {g2.x, g2.y, g2.z, g2.w}, gg3[4] = {g3.x, g3.y, g3.z, g3.w};
     // (w_k, a_k) at the first and last cell of the quad from the table, linear in between (R is linear in the cell
     // index to 1e-3 Mpc/h over four cells, the tabulated functions to ~1e-5)
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(256, 3) draw_qso_fast_kernel(const smk_qso_par
       const float pt = fmaf(fmaf(s, wq[1][0] - wq[0][0], wq[0][0]), __expf(fmaf(s, aq[1][0] - aq[0][0], aq[0][0]) * gg1[j]),
                             fmaf(fmaf(s, wq[1][1] - wq[0][1], wq[0][1]), __expf(fmaf(s, aq[1][1] - aq[0][1], aq[0][1]) * gg2[j]),
                                  fmaf(s, wq[1][2] - wq[0][2], wq[0][2]) * __expf(fmaf(s, aq[1][2] - aq[0][2], aq[0][2]) * gg3[j])));
-      if ((float)c[j] * 2.3283064365386963e-10f < pt) hit |= 1u << j;            // cond1: u < norm * ptot
+      if (cond1_uniform(c[j]) < pt) hit |= 1u << j;                              // cond1: u < norm * ptot
     }
     if (!hit) continue;
     const double bz1 = bias_qso(p.z1), bz2 = bias_qso(p.z2), bz3 = bias_qso(p.z3);

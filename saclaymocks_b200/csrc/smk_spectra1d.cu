@@ -135,27 +135,35 @@ __global__ void fgpa_kernel(size_t n, int npix, const float* __restrict__ delta_
 
 }  // namespace smk
 
-// twiddle tables for the 1-D transforms are cached per nfft in the library (tiny: <= 64 KB)
-static float2* g_tw1d[16] = {nullptr};
+// twiddle tables for the 1-D transforms are cached per (device, nfft) in the library (tiny: <= 64 KB each)
+#include <mutex>
+static std::mutex g_tw1d_mutex;
+static float2* g_tw1d[64][16] = {};
 
-static int tw1d(int nfft, const float2** out) {
-  int lg = 0;
+int smk_tw1d(int nfft, const float2** out) {
+  int lg = 0, dev = 0;
   while ((1 << lg) < nfft) ++lg;
-  if (!g_tw1d[lg]) {
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || lg >= 16) {
+    smk::set_error("twiddle cache: bad device or transform length");
+    return SMK_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lock(g_tw1d_mutex);
+  if (!g_tw1d[dev][lg]) {
     float2* h = new float2[nfft];
     for (int k = 0; k < nfft; ++k) {
       double ang = -2.0 * M_PI * (double)k / (double)nfft;
       h[k] = make_float2((float)cos(ang), (float)sin(ang));
     }
-    cudaError_t e = cudaMalloc(&g_tw1d[lg], nfft * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMemcpy(g_tw1d[lg], h, nfft * sizeof(float2), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMalloc(&g_tw1d[dev][lg], nfft * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpy(g_tw1d[dev][lg], h, nfft * sizeof(float2), cudaMemcpyHostToDevice);
     delete[] h;
     if (e != cudaSuccess) {
       smk::set_error(std::string("twiddle upload: ") + cudaGetErrorString(e));
+      g_tw1d[dev][lg] = nullptr;
       return SMK_ERR_CUDA;
     }
   }
-  *out = g_tw1d[lg];
+  *out = g_tw1d[dev][lg];
   return SMK_OK;
 }
 
@@ -166,7 +174,7 @@ extern "C" int smk_smallscale(smk_ctx* ctx, int nqso, int nfft, int npix, const 
   if (nqso == 0) return SMK_OK;
   if (!filt_rows || !row_of_qso || !delta_s || npix > nfft) { set_error("smk_smallscale: bad argument"); return SMK_ERR_ARG; }
   SmallScaleParams p{nqso, npix, noise, seed, filt_rows, row_of_qso, sig_pix, sig_eff, delta_s, qso_ids, nullptr};
-  int rc = tw1d(nfft, &p.tw);
+  int rc = smk_tw1d(nfft, &p.tw);
   if (rc) return rc;
   cudaStream_t st = smk_ctx_stream(ctx);
   switch (nfft) {

@@ -80,6 +80,7 @@ class SkewerEngine(object):
         self.geom = geom
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.rvec = torch.as_tensor(geom.R_vec, dtype=torch.float64, device=self.device)
+        self.ctx = _lib.StreamCtx(self.device)
 
     def read_spec(self, fields, xyzr, nforest, ix0=0, xmin=None, xmax=None, rsd=True, dla=True, out=None):
         """Batched ReadSpec over one slab.  fields: dict name -> device float32 [nxs, NY, NZ].
@@ -103,7 +104,7 @@ class SkewerEngine(object):
         q = torch.as_tensor(np.ascontiguousarray(xyzr, dtype=np.float64), device=self.device)
         nf = torch.as_tensor(np.ascontiguousarray(nforest, dtype=np.int32), device=self.device)
         cg = g.c_geom()
-        _lib.check(self.lib.smk_skewers(None, C.byref(cg), fl, int(ix0), int(nxs), C.c_double(xmin), C.c_double(xmax),
+        _lib.check(self.lib.smk_skewers(self.ctx.handle(), C.byref(cg), fl, int(ix0), int(nxs), C.c_double(xmin), C.c_double(xmax),
                                         int(rsd), int(dla), nq, _ptr(q), _ptr(nf), _ptr(self.rvec), npix,
                                         _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
         return out
@@ -117,6 +118,7 @@ class FGPA(object):
         self.geom = geom
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.pixsize = pixsize
+        self.ctx = _lib.StreamCtx(self.device)
         # merge_spectra.py:285-288: z is FLOAT32 in both modes (zfix * ones_like(float32 LAMBDA), or the float32
         # REDSHIFT HDU).  Kept: with -zfix 2.4 the float32 value 2.4000001 and the float32 pairwise mean of the forest
         # decide the tie between the tabulated P1D_miss redshifts 2.2 and 2.6.
@@ -167,7 +169,7 @@ class FGPA(object):
             idx = n0 + j
             ok = (idx >= 0) & (idx < npix)
             v = lam32[np.clip(idx, 0, npix - 1)] / one_plus
-            cnt += (ok & (v < np.float32(constant.lya)) & (v > np.float32(constant.lylimit))) | (ok & (j < 0) & False)
+            cnt += ok & (v < np.float32(constant.lya)) & (v > np.float32(constant.lylimit))
         return np.clip(n0 - 3, 0, npix) + cnt
 
     def zeff(self, nforest):
@@ -192,7 +194,7 @@ class FGPA(object):
         if noise is not None:
             nz_t = torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32), device=self.device)
             assert tuple(nz_t.shape) == (nq, nfft)
-        _lib.check(self.lib.smk_smallscale(None, nq, nfft, npix, _ptr(nz_t), C.c_uint64(seed), _ptr(self.filt_rows(nfft)),
+        _lib.check(self.lib.smk_smallscale(self.ctx.handle(), nq, nfft, npix, _ptr(nz_t), C.c_uint64(seed), _ptr(self.filt_rows(nfft)),
                                            _ptr(rows_t), _ptr(self.sig_pix), _ptr(sig_eff_t), _ptr(ids_t), _ptr(d)))
         return d                  # rows of empty forests are zeroed by the kernel (row_of_qso = -1)
 
@@ -214,6 +216,6 @@ class FGPA(object):
     def flux(self, delta_l, delta_s=None, eta_par=None):
         nq, npix = delta_l.shape
         F = torch.empty_like(delta_l)
-        _lib.check(self.lib.smk_fgpa(None, nq, npix, _ptr(delta_l), _ptr(delta_s), _ptr(eta_par), _ptr(self.G),
+        _lib.check(self.lib.smk_fgpa(self.ctx.handle(), nq, npix, _ptr(delta_l), _ptr(delta_s), _ptr(eta_par), _ptr(self.G),
                                      _ptr(self.a), _ptr(self.b), _ptr(self.c), _ptr(F)))
         return F

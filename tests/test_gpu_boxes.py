@@ -134,6 +134,19 @@ def test_fused_philox_equals_unfused(cuda):
     bs.close()
 
 
+def test_philox_noise_matches_host_restatement(cuda):
+    """smk_noise_philox against a numpy restatement of Philox4x32-10 (itself pinned to the Random123 known-answer
+    vectors, tests/test_philox_cpu.py) + Box-Muller.  The device uses __logf / __sincosf: 2e-5 absolute."""
+    from helpers import philox_normals_np
+    from saclaymocks_b200.boxes import BoxSynth
+    bs = BoxSynth(16, 16, 24, 8.0, device=cuda)
+    for seed in (0, 123, (7 << 32) + 5):
+        got = bs.noise_philox(seed).cpu().numpy().ravel()
+        ref = philox_normals_np(seed, got.size)
+        assert np.max(np.abs(got - ref)) < 2e-5, seed
+    bs.close()
+
+
 def test_unsupported_shape_fails_loudly(cuda):
     from saclaymocks_b200 import _lib
     from saclaymocks_b200.boxes import BoxSynth

@@ -148,3 +148,37 @@ def test_gpu_fast_kernel_probability_matches_oracle_ptot(cuda):
     assert abs(np.mean(nn) - expected) < 5 * np.sqrt(expected / len(nn)), (nn, expected)
     assert len(set(nn)) > 1                                                  # different seeds, different draws
     bs.close()
+
+
+def test_gpu_fast_kernel_selects_the_exact_kernels_quasars(cuda, monkeypatch):
+    """Production kernel (tabulated float32 ptot) against the reference-arithmetic kernel on the SAME Philox variates
+    (both take cond1's variate from cond1_block(), smk_qso.cu): the two selections are identical except for cells
+    whose variate falls inside the float32 / table error of norm * ptot (relative 1e-4: a handful out of ~1e4 cond1
+    survivors); every quasar selected by both has bit-identical float64 records (same finish_cell())."""
+    from saclaymocks_b200 import qso
+    from saclaymocks_b200.boxes import BoxSynth
+    rng = np.random.default_rng(10)
+    NXs, NY, NZ, dcell = 32, 64, 384, 8.76
+    boxes = {k: (0.9 * rng.standard_normal((NXs, NY, NZ))).astype(np.float32) for k in ("boxln_1", "boxln_2", "boxln_3")}
+    boxes.update({k: (300 * rng.standard_normal((NXs, NY, NZ))).astype(np.float32) for k in ("vx", "vy", "vz")})
+    sig = tuple(float(np.std(boxes[k])) for k in ("boxln_1", "boxln_2", "boxln_3"))
+    st = qso.QsoSetup(NXs, NY, NZ, 64, dcell, 1, 2, 190.0, 5.0, 30.0, 30.0, 1.8, 3.6, sig,
+                      rho_sum=qso.scaled_rho_sum(NXs * NY * NZ) / 50)          # ~50x the nominal density
+    bs = BoxSynth(16, 16, 24, 2.19, device=cuda)
+    dev = {k: torch.as_tensor(v, device=cuda) for k, v in boxes.items()}
+    d = qso.QsoDrawer(bs)
+    a = ([dev["boxln_1"], dev["boxln_2"], dev["boxln_3"]], [dev["vx"], dev["vy"], dev["vz"]])
+    fast = d.draw(st, *a, ix0=NXs, seed=21)
+    monkeypatch.setenv("SMK_QSO_EXACT", "1")
+    exact = d.draw(st, *a, ix0=NXs, seed=21)
+    monkeypatch.delenv("SMK_QSO_EXACT")
+    kf = {tuple(c): i for i, c in enumerate(fast["cells"])}
+    ke = {tuple(c): i for i, c in enumerate(exact["cells"])}
+    common = sorted(set(kf) & set(ke))
+    odd = set(kf) ^ set(ke)
+    assert len(exact["RA"]) > 3000
+    assert len(odd) <= max(3, 2e-3 * len(ke)), (len(odd), len(ke))
+    assert abs(fast["nn_cond1"] - exact["nn_cond1"]) <= max(5, 2e-3 * exact["nn_cond1"])
+    fi, ei = [kf[c] for c in common], [ke[c] for c in common]
+    assert np.array_equal(fast["f64"][fi], exact["f64"][ei])
+    bs.close()

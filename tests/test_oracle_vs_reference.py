@@ -130,9 +130,9 @@ def test_c1_end_to_end(golden_c1):
     _end_to_end(golden_c1)
 
 
-def test_c2_end_to_end(golden_c2):
+def test_c2_end_to_end(golden_c2_slow):
     """BASELINE config 2, the bench workload, at full size (512 x 512 x 1536): minutes of CPU work, SMK_SLOW_TESTS=1."""
-    _end_to_end(golden_c2)
+    _end_to_end(golden_c2_slow)
 
 
 def _end_to_end(g):
