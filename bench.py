@@ -5,9 +5,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--box NX] [--impl reference]
 
 Prints ONE JSON line (see the driver contract in the task statement).  `value` = chunk cells / device time of the
-whole step with inputs resident in HBM; `e2e` = same through host buffers (pinned weights in, every box and
-every spectrum row copied back); `roofline` = the slowest FFT pass kernel against the measured HBM copy peak;
-`cpu_baseline` = the CPU oracle (restated reference, scipy.fft + numba) on a bounded sample on this host.
+whole step with inputs resident in HBM; `e2e` = same through host buffers (pinned inputs in, every box and
+every spectrum row copied back); `roofline` = the kernel with the largest share of the step (FFT passes against the
+measured HBM copy peak, the skewer gather against the FP32 peak and the HBM byte model), every hot kernel listed under
+`roofline.kernels`; `cpu_baseline` = the CPU oracle (restated reference, scipy.fft + numba) on a bounded sample on this
+host; `parity_selfcheck` (N > 1) = sharded vs single-GPU pipeline on the same seeded thin box, run before timing.
 """
 import argparse
 import json
@@ -62,7 +64,28 @@ def weight_tables_device(bs, device):
     return {name: bs.weight_table(name) for name in ("Pln1", "Pln2", "Pln3", "P0")}
 
 
-WEAK_BOX = {1: (512, 512), 2: (1024, 512), 4: (1024, 1024), 8: (2048, 1024)}   # per-GPU cells fixed (weak scaling)
+# The configuration BASELINE.json names for each GPU count: config 2 (one 512 x 512 x 1536 chunk) on one GPU, config 3
+# (box-size 1024) on 2 and 4 GPUs, config 4 (the nominal 2560 x 2560 x 1536 chunk) on 8 GPUs.  `--weak` selects the
+# round-1 boxes with a fixed number of cells per GPU instead.
+CONFIG_BOX = {1: (512, 512), 2: (1024, 1024), 4: (1024, 1024), 8: (2560, 2560)}
+WEAK_BOX = {1: (512, 512), 2: (1024, 512), 4: (1024, 1024), 8: (2048, 1024)}
+FP32_FLOP_PER_PIXEL = 343 * 11 * 2      # literal ReadSpec: 343 weights x (10 fields + the weight sum), SURVEY.md 8(d)
+SKEWER_BYTES_PER_PIXEL = 191.0          # 17.9 B/pixel/field x 10 fields + 12 B of outputs, SURVEY.md 8(d)
+
+
+def box_for(world, args):
+    if args.box:
+        return args.box, args.box
+    return (WEAK_BOX if args.weak else CONFIG_BOX)[world]
+
+
+def workload_config(nx, ny, world):
+    """The `config` object of the JSON line: identical in the GPU arm and the reference arm."""
+    nqso = len(synthetic_qsos(nx, ny)[0])
+    return {"workload": workload_name(nx, ny, nqso), "box": [nx, ny, NZ], "nqso": int(nqso),
+            "cells_per_gpu": nx * ny * NZ // world,
+            "l2": "every pass streams >= 1.6 GB per launch, far above the 126 MB L2; no flush needed",
+            "parallelism": "x-slabs over %d GPU(s), one exchange per 3-D transform" % world}
 
 
 def workload_name(nx, ny, nqso):
@@ -167,45 +190,55 @@ def cpu_oracle_step(nx, workers, nq_per_worker=24, skewer_procs=None):
     from oracle import spectra as osp
     geom = osp.Geometry(nx, nx, NZ, dcell)
     npx_full = int(np.searchsorted(geom.lambda_vec, 1215.67 * (1 + z.astype(np.float64))).sum())
-    t_skew = npx_full / rate
+    t_skew = npx_full / rate if rate > 0 else 0.0
     cells = nx * nx * NZ
     return {"cells": cells, "t_boxes": t_boxes, "t_skewers_extrapolated": t_skew, "skewer_pixels_per_s": rate,
             "npix_sampled": npx, "npix_full": npx_full, "setup_s": t1 - t0,
             "value": cells / (t_boxes + t_skew)}
 
 
+REF_SAMPLE_NX = 256          # the CPU sample: a 256 x 256 x 1536 box (the size that is kinder to the CPU than 128)
+REF_TIME_BUDGET_S = 200.0    # the reference arm stops timing new steps once this much wall time has been spent
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (restated as the oracle: the reference is
-    Python and its FFTW/fitsio/healpy wheels are absent) on all host cores."""
+    Python and its FFTW/fitsio/healpy wheels are absent) on all host cores.  Every step is the SAME bounded
+    sample -- a 256 x 256 x 1536 box through all 13 products plus full-density skewers -- whatever --steps says; the
+    number of timed steps is capped by a wall-time budget instead of shrinking the sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count()
-    # bounded sample per step: a 256 x 256 x 1536 box (~15 s per step on 16 cores; the larger sample is the one that is
-    # kinder to the CPU: 6.9e6 cells/s against 4.1e6 cells/s on a 128 x 128 x 1536 box), the smaller box when the driver
-    # asks for so many steps that the run would not end within a few minutes
-    nx = 256 if args.steps + args.warmup <= 10 else 128
+    nx = REF_SAMPLE_NX
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    bx, by = (args.box, args.box) if args.box else WEAK_BOX.get(world, WEAK_BOX[1])
-    nqso = len(synthetic_qsos(bx, by)[0])
-    vals, times = [], []
-    for i in range(args.warmup + args.steps):
+    bx, by = box_for(world, args)
+    t_start = time.time()
+    cpu_oracle_step(32, cores, nq_per_worker=4, skewer_procs=min(cores, 4))        # imports, numba compilation
+    nwarm = min(args.warmup, 1)
+    vals, times, steps_timed = [], [], 0
+    for i in range(nwarm + args.steps):
         t0 = time.time()
-        r = cpu_oracle_step(nx, cores, nq_per_worker=8 if nx < 256 else 24)
-        if i >= args.warmup:
+        r = cpu_oracle_step(nx, cores)
+        if i >= nwarm:
             vals.append(r["value"])
             times.append(time.time() - t0)
+            steps_timed += 1
+            if time.time() - t_start + times[-1] > REF_TIME_BUDGET_S:
+                break
     v = float(np.mean(vals))
     sample = ("each step = a %dx%dx1536 box of the same workload: 13 products (scipy.fft float32, workers=%d) + numba "
-              "ReadSpec on %d quasars/core extrapolated to that box's full-density catalogue; cells/s of the sample "
+              "ReadSpec on 24 quasars/core extrapolated to that box's full-density catalogue; cells/s of the sample "
               "stand for the workload's (FFT cost per cell grows only logarithmically with the box); pocketfft stands "
-              "in for FFTW (pyfftw is not installable)" % (nx, nx, cores, 8 if nx < 256 else 24))
+              "in for FFTW (pyfftw is not installable); %d of the %d requested steps timed (wall-time budget %.0f s, "
+              "%d warm-up)" % (nx, nx, cores, steps_timed, args.steps, REF_TIME_BUDGET_S, nwarm))
     line = {"impl": "reference", "metric": "grf_cells_per_s", "value": v, "unit": "cells/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+            "steps": args.steps, "warmup": args.warmup, "steps_timed": steps_timed,
+            "ms_per_step": 1e3 * float(np.mean(times)),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(bx, by, nqso), "box": [bx, by, NZ], "nqso": int(nqso),
-                       "sample_box": [nx, nx, NZ]},
-            "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(bx, by, world),
+            "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
+                             "sample_box": [nx, nx, NZ]},
             "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -226,11 +259,72 @@ def emit(real_fd, text):
     os.write(real_fd, (text + "\n").encode())
 
 
+def parity_selfcheck(world, rank, dev, nx):
+    """Sharded pipeline against the single-GPU pipeline on the same seeded input, run by every rank before the timed
+    region (N > 1): a thin box with the benched x and z transform lengths and the real geometry (nx x 64 x 1536 cells
+    of 2.19 Mpc/h, Philox noise, GPU weight tables), all 13 products and the skewer rows of 96 sightlines spread over
+    every slab (halo exchange included).  The single-GPU result is itself held
+    to the CPU oracle by tests/ (-m gpu); this check carries that parity over to the sharded configuration the SCALE
+    line is measured on.  Returns the worst relative L2 over products and ranks and the worst row difference."""
+    import torch
+    import torch.distributed as dist
+    from saclaymocks_b200.boxes import PRODUCTS
+    from saclaymocks_b200.chunk import ChunkPipeline
+    ny, nz, dcell = 64, NZ, DCELL
+    rng = np.random.default_rng(5)
+    nq = 96
+    res = {}
+    outs = []
+    for nr, rk in ((world, rank), (1, 0)):
+        pipe = ChunkPipeline(nx, ny, nz, dcell, device=dev, rank=rk, nranks=nr)
+        pipe.set_weights({k: pipe.bs.weight_table(k) for k in ("Pln1", "Pln2", "Pln3", "P0")})
+        if not outs:
+            g = pipe.geom
+            half = np.degrees(np.arctan((g.LX / 2 - 4 * dcell) / (g.R0 + g.LZ / 2))) * 0.95
+            half_y = np.degrees(np.arctan((g.LY / 2 - 4 * dcell) / (g.R0 + g.LZ / 2))) * 0.9
+            ra = (190.0 + rng.uniform(-half, half, nq)).astype("f4")
+            dec = rng.uniform(-half_y, half_y, nq).astype("f4")
+            z = rng.uniform(2.0, 3.55, nq).astype("f4")
+        pipe.set_catalogue(ra, dec, z, 190.0, 0.0)
+        pipe.step_boxes(seed=1234)
+        pipe.step_skewers(seed=1234)
+        torch.cuda.synchronize()
+        outs.append(pipe)
+    sh, one = outs
+    nxl = nx // world
+    worst = 0.0
+    for name in PRODUCTS:
+        a = sh.interior(name).double()
+        b = one.interior(name)[rank * nxl:(rank + 1) * nxl].double()
+        worst = max(worst, float(((a - b) ** 2).sum().sqrt() / (b ** 2).sum().sqrt()))
+    rows = 0.0
+    npx = 0
+    sel_one = list(one.cat["sel"])
+    for i, q in enumerate(sh.cat["sel"]):
+        j = sel_one.index(q)
+        for k in (0, 1, 3):                                   # delta_l, eta_par, flux
+            a, b = sh.out[k][i], one.out[k][j]
+            m = ~torch.isnan(a) & (one.out[0][j] > -1e5)
+            if bool(m.any()):
+                rows = max(rows, float((a[m] - b[m]).abs().max()))
+                npx += int(m.sum()) if k == 0 else 0
+    t = torch.tensor([worst, rows], dtype=torch.float64, device=dev)
+    n = torch.tensor([npx], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(n)
+    del sh, one, outs
+    torch.cuda.empty_cache()
+    worst, rows = (float(v) for v in t.cpu())
+    return {"what": "sharded (%d ranks, fused exchange) vs single-GPU pipeline, same Philox seed" % world,
+            "box": [nx, ny, nz], "products": len(PRODUCTS), "max_rel_l2_boxes": worst, "max_abs_rows": rows,
+            "forest_pixels_compared": int(n.item()), "tol_boxes": 1e-5, "tol_rows": 1e-5,
+            "ok": bool(worst < 1e-5 and rows < 1e-5 and int(n.item()) > 1000)}
+
+
 def run_gpu(args):
     real_stdout = quiet_stdout()
     import torch
     import torch.distributed as dist
-    from saclaymocks_b200 import spectra as sp
     from saclaymocks_b200.chunk import ChunkPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,11 +334,10 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # weak scaling: per-GPU work fixed at one 512 x 512 x 1536 chunk's worth of cells
-    if args.box:
-        nx = ny = args.box
-    else:
-        nx, ny = WEAK_BOX[world]
+    nx, ny = box_for(world, args)
+    selfcheck = None
+    if world > 1 and not args.no_selfcheck:
+        selfcheck = parity_selfcheck(world, rank, dev, nx)
     pipe = ChunkPipeline(nx, ny, NZ, DCELL, device=dev, rank=rank, nranks=world)
     W = weight_tables_device(pipe.bs, dev)
     ra, dec, z, ra0, dec0 = synthetic_qsos(nx, ny)
@@ -259,11 +352,20 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def per_rank(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(v)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     # ---- device-resident arm
     for _ in range(args.warmup):
         pipe.step(seed=42)
     barrier()
     pipe.bs.timing_enable(True)
+    pipe.gather_events = []
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     with ClockSampler(local) as clk:
         barrier()
@@ -279,14 +381,18 @@ def run_gpu(args):
         wall = time.time() - t0
     passes = pipe.bs.timing_collect()
     pipe.bs.timing_enable(False)
+    t_gather = float(np.mean([a.elapsed_time(b) for a, b in pipe.gather_events])) if pipe.gather_events else 0.0
+    pipe.gather_events = None
     t_box = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
     t_skw = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)) / args.steps
     t_tot = ev[0].elapsed_time(ev[3 * args.steps]) / args.steps
-    t = torch.tensor([t_tot, t_box, t_skw], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_tot, t_box, t_skw = (float(v) for v in t.cpu())
-    npx = pipe.forest_pixels_total()
+    # per-rank stage times: a rank's skewer interval starts when ITS boxes are done, so max(boxes) + max(skewers) may
+    # exceed the step; the per-rank lists show who waits for whom
+    box_r, skw_r, gat_r = per_rank(t_box), per_rank(t_skw), per_rank(t_gather)
+    pix_r = [int(v) for v in per_rank(pipe.cat["own_pixels"])]
+    nq_r = [int(v) for v in per_rank(len(pipe.cat["sel"]))]
+    t_tot = max(per_rank(t_tot))
+    npx = int(sum(pix_r))
 
     # ---- quasar drawing on the resident boxes (reported beside the step, not part of `value`)
     pipe.draw_qso(seed=1)
@@ -298,12 +404,11 @@ def run_gpu(args):
     barrier()
     t_qso = 1e3 * (time.time() - tq) / max(1, min(args.steps, 3))
 
-    # ---- end-to-end arm: pinned host inputs in, all boxes + all spectra rows back to host, every step.  With several
-    #      ranks every rank stages its own x-slabs and rows over its own PCIe link; the time is taken between two
-    #      barriers (= the slowest rank) and the byte counts are summed over the ranks.
+    # ---- end-to-end arm: pinned host inputs in, all boxes + all spectra rows back to host, every step, through the
+    #      same pipelined step as above.  With several ranks every rank stages its own x-slabs and rows over its own
+    #      PCIe link; the time is taken between two barriers (= the slowest rank), byte counts are summed over ranks.
     e2e = None
-    slab_bytes = pipe.bs.nxl * pipe.bs.NY * pipe.bs.NZ * 4
-    if not args.no_e2e and (slab_bytes <= (2 << 30) or args.e2e):
+    if not args.no_e2e:
         host = pipe.make_host_buffers(W)
         pipe.step_e2e(host, seed=7)
         barrier()
@@ -332,36 +437,68 @@ def run_gpu(args):
                "ms_per_step": 1e3 * dt, "steps": n_e2e, "skewer_pixels_per_s": npx / dt,
                "what": "P(k) splines + sightline catalogue in from pinned host memory (weight tables evaluated on the "
                        "GPU inside the step), all 13 boxes and the four spectra arrays of every rank copied back to "
-                       "pinned host memory (PCIe-bound)"}
+                       "pinned host memory through two 1 GiB staging buffers per rank (PCIe-bound); same pipelined "
+                       "step as the device-resident arm (fused exchange at N > 1)"}
         e2e["resident"] = {"value": cells / dtr, "unit": "cells/s", "ms_per_step": 1e3 * dtr,
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_res,
                            "what": "same chunk with the boxes kept in HBM: P(k) splines + sightlines in, quasars drawn on "
-                                   "the resident boxes (smk_draw_qso), quasar table + spectra rows out"}
+                                   "the resident boxes (smk_draw_qso), quasar table + spectra rows out (the boxes, which "
+                                   "make_boxes.py writes to disk, do NOT reach the host in this variant)"}
         del host
 
-    # ---- roofline of the dominant kernel (slowest FFT pass), algorithmic bytes per launch
+    # ---- roofline: every hot kernel against its bound, the one with the largest share of the step as the headline
     peak, how = measured_peak_hbm()
     nk_bytes = pipe.bs.NX * pipe.bs.nyl * pipe.bs.nzh * 8          # this rank's half-complex box
     nr_bytes = pipe.bs.nxl * pipe.bs.NY * pipe.bs.NZ * 4           # this rank's real box
     alg = {"inv_x": 2 * nk_bytes + (4.0 / 13.0) * nk_bytes / 2, "inv_y": 2 * nk_bytes, "c2r_z": nk_bytes + nr_bytes,
            "r2c_z": nk_bytes, "fwd_y": 2 * nk_bytes, "fwd_x": 2 * nk_bytes}
     per = {k: (ms / n if n else 0.0) for k, (ms, n) in passes.items()}
-    dom = max(("inv_x", "inv_y", "c2r_z"), key=lambda k: per[k])
-    achieved = alg[dom] / (per[dom] * 1e-3) / 1e9 if per[dom] else 0.0
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (512 x 512 x 1536 only)
-    traffic = None
-    tfile = next((f for f in (os.path.join(ROOT, "profiles", "traffic_%s.json" % t) for t in ("r01d", "r01b", "r01"))
-                  if os.path.isfile(f)), "")
-    if os.path.isfile(tfile) and (nx, ny, world) == (512, 512, 1):
-        tj = json.load(open(tfile))
-        key = {"c2r_z": "c2r_z_kernel<768>", "inv_y": "c2c_strided_kernel<512, 1, 0, 0, 0>",
-               "inv_x": "c2c_strided_kernel<512, 1, 1, 0, 0>"}[dom]
-        traffic = tj.get(key)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": how,
-                "passes_ms": per, "passes_gbs": {k: (alg[k] / (per[k] * 1e-3) / 1e9 if per[k] else None) for k in per},
-                "chunk_gbs": (332.0 * cells / world) / (t_box * 1e-3) / 1e9}
+    kernels = {}
+    for k in ("inv_x", "inv_y", "c2r_z"):
+        if per[k]:
+            g = alg[k] / (per[k] * 1e-3) / 1e9
+            kernels[k] = {"bound": "hbm", "ms_per_launch": per[k], "launches_per_step": 13, "ms_per_step": 13 * per[k],
+                          "achieved": g, "peak": peak, "unit": "GB/s", "frac": g / peak}
+    traffic_all, traffic_src = {}, None
+    for tag in ("r02",):
+        tf = os.path.join(ROOT, "profiles", "traffic_%s.json" % tag)
+        if os.path.isfile(tf) and (nx, ny, world) == (512, 512, 1):
+            traffic_all, traffic_src = json.load(open(tf)), "profiles/traffic_%s.json (ncu --set full of this workload)" % tag
+    sm_mhz_max = clk.summary()["sm_max_mhz"] or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz_max * 1e6 / 1e12            # TFLOP/s: SMs x FMA lanes x 2 x max SM clock
+    ig = int(np.argmax(gat_r))              # the rank whose gather takes longest (the fullest slab)
+    if gat_r[ig] > 0:
+        px0, t_gather = pix_r[ig], gat_r[ig]
+        gbs = SKEWER_BYTES_PER_PIXEL * px0 / (t_gather * 1e-3) / 1e9
+        tfl = FP32_FLOP_PER_PIXEL * px0 / (t_gather * 1e-3) / 1e12
+        kernels["skewers"] = {"bound": "fp32", "ms_per_launch": t_gather, "launches_per_step": 1, "ms_per_step": t_gather,
+                              "achieved": tfl, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tfl / fp32_peak,
+                              "peak_source": "nominal: 148 SMs x 128 FMA lanes x 2 x %.0f MHz" % sm_mhz_max,
+                              "flop_per_pixel": FP32_FLOP_PER_PIXEL, "pixels": int(px0),
+                              "hbm_model": {"bytes_per_pixel": SKEWER_BYTES_PER_PIXEL, "achieved": gbs, "peak": peak,
+                                            "unit": "GB/s", "frac": gbs / peak}}
+    names = {"c2r_z": "c2r_z_kernel", "inv_y": "c2c_strided_kernel<inverse y>", "inv_x": "c2c_strided_kernel<inverse x, fused multiply>",
+             "skewers": "skewers gather (smk_skewers_fgpa)"}
+    for k, v in kernels.items():
+        v["traffic"] = traffic_all.get(k)
+    if not kernels:
+        kernels["none"] = {"bound": "hbm", "ms_per_step": 0.0, "achieved": 0.0, "peak": peak, "unit": "GB/s", "frac": 0.0}
+        names["none"] = "no kernel timed"
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    roofline = dict(kernels[dom])
+    roofline.update({"kernel": dom, "kernel_name": names[dom], "peak_source": kernels[dom].get("peak_source", how),
+                     "traffic_source": traffic_src, "kernels": kernels,
+                     "passes_ms": per, "passes_gbs": {k: (alg[k] / (per[k] * 1e-3) / 1e9 if per.get(k) else None) for k in alg},
+                     "chunk_gbs": (332.0 * cells / world) / (max(box_r) * 1e-3) / 1e9,
+                     "chunk_frac": (332.0 * cells / world) / (max(box_r) * 1e-3) / 1e9 / peak})
     if world > 1:
+        # serial HBM + NVLink model of the box stage: 332 B/cell of HBM traffic per rank at the measured
+        # copy peak + 14 exchanges of (N-1)/N of this rank's half-complex box at the measured 770 GB/s per direction
+        t_hbm = 332.0 * cells / world / (peak * 1e9) * 1e3
+        t_nvl = 14 * (world - 1) / world * nk_bytes / 770e9 * 1e3
+        roofline["boxes_model_ms"] = {"hbm": t_hbm, "nvlink": t_nvl, "serial": t_hbm + t_nvl, "overlapped": max(t_hbm, t_nvl),
+                                      "frac_serial": (t_hbm + t_nvl) / max(box_r),
+                                      "frac_overlapped": max(t_hbm, t_nvl) / max(box_r)}
         roofline["note"] = ("N > 1: the x pass runs on a second stream against the y / z passes of the previous product, "
                             "so the per-pass intervals overlap and each is inflated by the other stream's kernels; the "
                             "single-GPU line carries the per-kernel roofline")
@@ -370,25 +507,29 @@ def run_gpu(args):
         cpu = None
         if not args.no_cpu and world == 1:          # the CPU baseline is reported at N=1 only
             cores = os.cpu_count()
-            r = cpu_oracle_step(256, cores)
+            r = cpu_oracle_step(REF_SAMPLE_NX, cores)
             cpu = {"value": r["value"], "unit": "cells/s", "cores": cores, "kind": "port",
                    "sample": "256x256x1536 box (1/4 of the cells), 13 products with scipy.fft float32 workers=%d "
                              "(pocketfft stands in for FFTW: pyfftw is not installable) + numba ReadSpec on 24 "
                              "quasars/core extrapolated to the box's %d forest pixels" % (cores, r["npix_full"]),
+                   "sample_box": [REF_SAMPLE_NX, REF_SAMPLE_NX, NZ],
                    "t_boxes_s": r["t_boxes"], "t_skewers_s": r["t_skewers_extrapolated"],
                    "skewer_pixels_per_s": r["skewer_pixels_per_s"], "grf_cells_per_s_boxes": r["cells"] / r["t_boxes"]}
-        line = {"metric": "grf_cells_per_s", "value": world * cells / world / (t_tot * 1e-3), "unit": "cells/s",
+        line = {"metric": "grf_cells_per_s", "value": cells / (t_tot * 1e-3), "unit": "cells/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_tot,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(nx, ny, len(ra)), "box": [nx, ny, NZ], "nqso": int(len(ra)), "forest_pixels": int(npx),
-                           "l2": "every pass streams >= 1.6 GB per launch, far above the 126 MB L2; no flush needed",
-                           "parallelism": "x-slabs over %d GPU(s), all-to-all transposes" % world},
-                "grf_cells_per_s_boxes": cells / (t_box * 1e-3), "box_cells_per_s": 13 * cells / (t_box * 1e-3),
-                "skewer_pixels_per_s": npx / (t_skw * 1e-3), "t_boxes_ms": t_box, "t_skewers_ms": t_skw,
+                "config": workload_config(nx, ny, world), "forest_pixels": npx,
+                "grf_cells_per_s_boxes": cells / (max(box_r) * 1e-3), "box_cells_per_s": 13 * cells / (max(box_r) * 1e-3),
+                "skewer_pixels_per_s": npx / (max(skw_r) * 1e-3), "t_boxes_ms": max(box_r), "t_skewers_ms": max(skw_r),
+                "t_gather_ms": max(gat_r),
+                "per_rank": {"t_boxes_ms": box_r, "t_skewers_ms": skw_r, "t_gather_ms": gat_r, "forest_pixels": pix_r,
+                             "sightlines": nq_r,
+                             "skewer_pixels_max_over_mean": max(pix_r) / (sum(pix_r) / world) if npx else None,
+                             "t_skewers_max_over_mean": max(skw_r) / (sum(skw_r) / world) if sum(skw_r) else None},
                 "t_draw_qso_ms": t_qso, "t_draw_qso_kernel_ms": pipe._qso_drawer.last_kernel_ms,
                 "nqso_drawn_rank0": int(nq_drawn),
                 "wall_s": wall, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": pipe.launches_per_step * args.steps,
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, "parity_selfcheck": selfcheck}
         emit(real_stdout, json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -400,10 +541,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--box", type=int, default=0, help="NX=NY override (default: 512 per GPU, weak scaling)")
+    ap.add_argument("--box", type=int, default=0, help="NX=NY override (default: the BASELINE.json configuration of "
+                                                       "this GPU count: 512 / 1024 / 1024 / 2560 at 1 / 2 / 4 / 8)")
+    ap.add_argument("--weak", action="store_true", help="round-1 boxes with a fixed number of cells per GPU")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e", action="store_true", help="run the end-to-end arm even when a rank's slab exceeds 2 GiB "
-                                                       "(two pinned staging buffers of that size per rank)")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the sharded-vs-single-GPU parity check (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

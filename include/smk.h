@@ -136,6 +136,10 @@ int smk_exchange_create(smk_ctx* ctx, int nbuf);
 int smk_exchange_handle(smk_ctx* ctx, int buf, unsigned char handle[64]);
 int smk_exchange_connect(smk_ctx* ctx, int buf, const unsigned char* handles);
 void* smk_exchange_ptr(smk_ctx* ctx, int buf);
+/* The fused x pass is bound by NVLink, not by the SMs: nsm > 0 runs it as a persistent kernel on nsm CTAs (several
+ * tiles per CTA), which leaves the other SMs to the y / z passes of the previous product on another stream; 0 (default)
+ * launches one CTA per tile. */
+int smk_exchange_set_sms(smk_ctx* ctx, int nsm);
 int smk_synth_c2r_local_p2p(smk_ctx* ctx, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
                             int buf);
 int smk_synth_c2r_finish_p2p(smk_ctx* ctx, int buf, float* out_slab, double* stats);

@@ -40,14 +40,18 @@ class ChunkPipeline(object):
             self.fields[name] = torch.empty((bs.nxl + h, bs.NY, bs.NZ), dtype=torch.float32, device=device)
         self.stats = torch.zeros((len(PRODUCTS), 2), dtype=torch.float64, device=device)
         if nranks > 1:
-            # two exchange buffer pairs: the all-to-all of product p overlaps the x pass of p+1 and the y/z passes of p-1
-            n = bs.NX * bs.nyl * bs.pitch
-            self.sendbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
-            self.recvbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(2)]
-            self.sendbuf, self.recvbuf = self.sendbufs[0], self.recvbufs[0]
             # fused peer-store exchange (default) or the pipelined NCCL all-to-all (SMK_P2P=0); measurements of both in
             # profiles/README.md
             self.p2p = os.environ.get("SMK_P2P", "1") != "0"
+            n = bs.NX * bs.nyl * bs.pitch
+            # NCCL mode: two exchange buffer pairs (the all-to-all of product p overlaps the x pass of p+1 and the y/z
+            # passes of p-1).  Fused mode: only the forward transform goes through NCCL -- one send buffer, and the
+            # receive side is boxk itself (the forward x pass runs in place), 15 GB less per rank at the nominal size
+            npair = 1 if self.p2p else 2
+            self.sendbufs = [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(npair)]
+            self.recvbufs = ([self.boxk.view(-1)] if self.p2p else
+                             [torch.empty(n, dtype=torch.complex64, device=device) for _ in range(npair)])
+            self.sendbuf, self.recvbuf = self.sendbufs[0], self.recvbufs[0]
             if self.p2p:
                 self._connect_exchange()
         self.W = None
@@ -71,11 +75,16 @@ class ChunkPipeline(object):
             _lib.check(L.smk_exchange_connect(h, b, blob))
         self._xptr = [L.smk_exchange_ptr(h, b) for b in range(2)]
         self._tok = torch.zeros(1, dtype=torch.float32, device=self.device)
-        # SMK_X_SMS > 0: the x pass runs persistent on that many CTAs (libsmk) and on a high-priority stream, so that
-        # its CTAs are placed first and the y / z passes of the other stream fill the remaining SMs
-        prio = -1 if int(os.environ.get("SMK_X_SMS", "0") or 0) > 0 else 0
-        self._xstream = torch.cuda.Stream(device=self.device, priority=prio)
+        # x pass on a high-priority stream: its CTAs are placed first; with set_x_sms(n > 0) it runs persistent on n CTAs
+        # and the y / z passes of the other stream fill the remaining SMs (SMK_X_SMS = initial value, default 0 = off)
+        self._xstream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.set_x_sms(int(os.environ.get("SMK_X_SMS", "0") or 0))
         dist.barrier(group=self.group)
+
+    def set_x_sms(self, n):
+        """CTAs of the persistent fused-exchange x pass (smk_exchange_set_sms); 0 = one CTA per tile."""
+        _lib.check(self.bs.lib.smk_exchange_set_sms(self.bs.h, int(n)))
+        self.x_sms = int(n)
 
     def _stream_barrier(self):
         """Cross-rank barrier in stream order (a one-element all-reduce): when it completes on this rank's stream,
@@ -153,12 +162,17 @@ class ChunkPipeline(object):
             self._a2a()
             _lib.check(L.smk_synth_c2r_finish(bs.h, _ptr(self.recvbuf), _ptr(out), _ptr(st)))
 
-    def step_boxes(self, seed=0, noise=None, products=PRODUCTS):
+    def step_boxes(self, seed=0, noise=None, products=PRODUCTS, on_product=None):
+        """Forward transform + the inverse transform of every product.  on_product(name), if given, is called right
+        after the last kernel of that product has been enqueued on the current stream (the end-to-end arm hangs its
+        device-to-host copy of the finished box there)."""
         self.stats.zero_()
         self.forward(seed, noise)
         if self.nranks == 1:
             for name in products:
                 self.product(name)
+                if on_product is not None:
+                    on_product(name)
             return
         # software pipeline over the independent inverse transforms (boxk is read-only after the 'box' product has
         # stored boxk*P0 back, and the products before it only read it): x pass of p | all-to-all of p-1 | y,z of p-2
@@ -193,6 +207,8 @@ class ChunkPipeline(object):
                     _lib.check(L.smk_synth_c2r_finish_p2p(bs.h, slot, _ptr(self.interior(name)), _ptr(self.stats[pid])))
                     ev_yz[slot] = torch.cuda.Event()
                     ev_yz[slot].record(main)
+                    if on_product is not None:
+                        on_product(name)
             finally:                                   # whatever happened, the ctx goes back to the caller's stream
                 L.smk_set_stream(bs.h, C.c_void_p(main.cuda_stream))
                 main.wait_stream(X)
@@ -208,8 +224,12 @@ class ChunkPipeline(object):
                                                        async_op=True)
             if pending is not None:
                 self._finish(*pending)
+                if on_product is not None:
+                    on_product(pending[2])
             pending = (work, slot, name)
         self._finish(*pending)
+        if on_product is not None:
+            on_product(pending[2])
 
     def _finish(self, work, slot, name):
         work.wait()               # the compute stream waits for the exchange; the host does not block
@@ -264,9 +284,16 @@ class ChunkPipeline(object):
         args = (self.bs.h, C.byref(cg), fl, ix0, nxs, C.c_double(c["xmin"]), C.c_double(c["xmax"]), int(self.rsd),
                 int(self.dla), nq, _ptr(c["xyzr_d"]), _ptr(c["nfor_d"]), _ptr(self.eng.rvec), npix, _ptr(dl), _ptr(ep),
                 _ptr(vp))
+        timed = getattr(self, "gather_events", None)        # bench.py: CUDA events around the gather kernel
+        if timed is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         if os.environ.get("SMK_FUSED_FGPA", "1") != "0":
             _lib.check(L.smk_skewers_fgpa(*args, _ptr(ds), _ptr(self.fgpa.G), _ptr(self.fgpa.a), _ptr(self.fgpa.b),
                                           _ptr(self.fgpa.c), _ptr(F)))
+            if timed is not None:
+                e1.record()
+                timed.append((e0, e1))
         else:
             _lib.check(L.smk_skewers(*args))
             _lib.check(L.smk_fgpa(self.bs.h, nq, npix, _ptr(dl), _ptr(ds), _ptr(ep), _ptr(self.fgpa.G),
@@ -330,6 +357,8 @@ class ChunkPipeline(object):
 
     # ------------------------------------------------------------------ end-to-end through host buffers
     # (any number of ranks: every rank stages its own x-slab of each box and its own spectra rows over its own PCIe link)
+    STAGE_BYTES = 1 << 30      # pinned staging buffers of the end-to-end arm (two per rank)
+
     def make_host_buffers(self, W_dev):
         bs = self.bs
         from . import pk
@@ -339,13 +368,17 @@ class ChunkPipeline(object):
             pp[k] = (torch.from_numpy(br).pin_memory(), torch.from_numpy(co).pin_memory(),
                      torch.empty(br.shape, dtype=torch.float64, device=self.device),
                      torch.empty(co.shape, dtype=torch.float64, device=self.device))
+        slab = bs.nxl * bs.NY * bs.NZ
+        # the two pinned buffers stand for the FITS writer's staging area: a slab larger than a buffer streams through
+        # them piece by piece (every byte of every box still crosses PCIe inside the timed region)
+        nstage = min(slab, self.STAGE_BYTES // 4)
         host = {"pp": pp,
-                "box": [torch.empty((bs.nxl, bs.NY, bs.NZ), dtype=torch.float32).pin_memory() for _ in range(2)],
+                "box": [torch.empty(nstage, dtype=torch.float32).pin_memory() for _ in range(2)],
                 "spec": [torch.empty(self.out[0].shape, dtype=torch.float32).pin_memory() for _ in range(4)],
-                "copy_stream": torch.cuda.Stream(device=self.device)}
+                "copy_stream": torch.cuda.Stream(device=self.device), "npiece": 0}
         host["h2d_bytes"] = (sum(v[0].numel() * 8 + v[1].numel() * 8 for v in pp.values()) + self.cat["xyzr"].nbytes
                              + self.cat["nfor"].nbytes)
-        host["d2h_bytes"] = len(PRODUCTS) * bs.nxl * bs.NY * bs.NZ * 4 + 4 * self.out[0].numel() * 4
+        host["d2h_bytes"] = len(PRODUCTS) * slab * 4 + 4 * self.out[0].numel() * 4
         return host
 
     def step_e2e_resident(self, host, seed=0):
@@ -380,10 +413,10 @@ class ChunkPipeline(object):
 
     def step_e2e(self, host, seed=0):
         """Host inputs in (P(k) splines and the quasar catalogue, pinned), every box and every spectrum row out to
-        host memory.  The spectral weight tables are evaluated on the GPU (smk_pk_weights) inside the step.  The two
-        pinned box buffers stand for the FITS writer's staging area; copies overlap the next product's transforms.
-        With several ranks each product goes through the serial NCCL exchange (forward()/product()): the step is bound
-        by the PCIe copies of the slabs, which run on every rank's own link."""
+        host memory.  The spectral weight tables are evaluated on the GPU (smk_pk_weights) inside the step.  The boxes
+        go through the same pipeline as the device-resident step (step_boxes: fused exchange on several ranks); the
+        device-to-host copy of a finished box is enqueued on a copy stream and overlaps the next product's transforms.
+        The step is bound by PCIe: every rank moves its own x-slabs and rows over its own link."""
         main = torch.cuda.current_stream(self.device)
         cs = host["copy_stream"]
         self.stats.zero_()
@@ -395,15 +428,20 @@ class ChunkPipeline(object):
         c = self.cat
         c["xyzr_d"].copy_(torch.from_numpy(c["xyzr"]), non_blocking=True)
         c["nfor_d"].copy_(torch.from_numpy(c["nfor"]), non_blocking=True)
-        self.forward(seed)
-        evs = []
-        for i, name in enumerate(PRODUCTS):
-            self.product(name)
+
+        def copy_out(name):
             e = torch.cuda.Event()
             e.record(main)
             cs.wait_event(e)
+            flat = self.interior(name).reshape(-1)
+            step = host["box"][0].numel()
             with torch.cuda.stream(cs):
-                host["box"][i & 1].copy_(self.interior(name), non_blocking=True)
+                for o in range(0, flat.numel(), step):
+                    n = min(step, flat.numel() - o)
+                    host["box"][host["npiece"] & 1][:n].copy_(flat[o:o + n], non_blocking=True)
+                    host["npiece"] += 1
+
+        self.step_boxes(seed, on_product=copy_out)
         self.step_skewers(seed)
         e = torch.cuda.Event()
         e.record(main)

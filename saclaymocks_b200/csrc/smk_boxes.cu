@@ -56,8 +56,8 @@ struct StridedParams {
   // peer mode (fused exchange): output point k goes to rank k / aout.nsplit, into peer[rank] (that rank's receive
   // buffer, already offset to this rank's chunk) at (k % nsplit) * lo_stride + outer * outer_stride + column
   float2* peer[SMK_MAX_RANKS];
-  int pf_dist;   // L2 prefetch distance in tiles (0 = off): each CTA prefetches the input rows of tile id + pf_dist
   int nouter;    // tiles = (ncols / LINES) x nouter
+  int x_sms;     // fused-exchange pass only: run persistent on this many CTAs (0 = one CTA per tile)
 };
 
 // element offset of point n: plain stride, or the two-level [hi][lo] form left behind by an all-to-all
@@ -94,21 +94,6 @@ __device__ __forceinline__ void strided_tile(const StridedParams& p, const int t
                                             : (long long)col;
   const float2* __restrict__ inl = p.in + (outer * p.ain.outer_stride + in_col);
   float2* __restrict__ outl = p.out + (outer * p.aout.outer_stride + col);
-  if (!SPLIT_IN && p.pf_dist > 0) {
-    // The first stage exposes one full DRAM latency per CTA (60 % of the kernel in the ncu source view).  Pull the
-    // rows (one 128-B line each when LINES == 16) of the tile a later CTA will read into L2 now.
-    const int gx = p.ncols / LINES;
-    const long long id = (long long)outer * gx + tile_x + p.pf_dist;
-    const int ty = (int)(id / gx), tx = (int)(id - (long long)ty * gx);
-    if (ty < p.nouter) {
-      const float2* nxt = p.in + ((long long)ty * p.ain.outer_stride + (long long)tx * LINES);
-      for (int n = threadIdx.x; n < N; n += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + n * p.ain.lo_stride));
-      if (MUL == MUL_TABLE) {
-        const float* wn = p.mul.wt + ((long long)ty * p.mul.wt_outer_stride + min(tx * LINES, p.wcols - 1));
-        for (int n = threadIdx.x; n < N; n += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(wn + n * p.mul.wt_n_stride));
-      }
-    }
-  }
 
   // ---- fused multiply of make_boxes.py:247-429 (reference float32 rounding order), applied to the loaded element
   float wv[MUL == MUL_TABLE ? TPT0 : 1][MUL == MUL_TABLE ? R0 : 1];
@@ -219,17 +204,6 @@ __global__ void SMK_STRIDED_BOUNDS(N, MUL) c2c_strided_persistent_kernel(const _
   }
 }
 
-// CTAs of the persistent fused-exchange x pass (SMK_X_SMS, 0 = one CTA per tile)
-static int peer_grid_cap() {
-  static int cap = -1;
-  if (cap < 0) {
-    const char* e = getenv("SMK_X_SMS");
-    cap = e ? atoi(e) : 0;
-    if (cap < 0) cap = 0;
-  }
-  return cap;
-}
-
 template <int N, bool INV, int MUL, bool SPLIT_IN, int SPLIT_OUT>
 static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st) {
   constexpr int LINES = StridedTraits<N>::LINES;
@@ -240,7 +214,7 @@ static int launch_strided_t(const StridedParams& p, int nouter, cudaStream_t st)
   if (p.ncols % LINES) { set_error("strided pass: column count must be a multiple of the tile width"); return SMK_ERR_ARG; }
   dim3 grid(p.ncols / LINES, nouter);
   if constexpr (SPLIT_OUT == OUT_PEER) {
-    const int cap = peer_grid_cap();
+    const int cap = p.x_sms;
     if (cap > 0 && (long long)cap < (long long)grid.x * grid.y) {
       auto pkern = c2c_strided_persistent_kernel<N, INV, MUL, SPLIT_IN, SPLIT_OUT>;
       if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -287,17 +261,6 @@ static int launch_strided_n(bool inv, int mul, const StridedParams& p, int noute
 
 #define SMK_STRIDED_SIZES(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(2560)
 
-int prefetch_distance() {
-  static int d = -1;
-  if (d < 0) {
-    // tuning knob (tiles ahead).  Measured on B200 at 512 x 512 x 1536: no gain at any distance (y pass 0.645 ms
-    // without, 0.63-0.75 ms with; x pass with table 0.86 -> 1.13 ms), so the prefetch is off by default.
-    const char* e = getenv("SMK_PF_DIST");
-    d = e ? atoi(e) : 0;
-  }
-  return d;
-}
-
 int strided_tile_width(int n) {
 #define X(N_) if (n == N_) return StridedTraits<N_>::LINES;
   SMK_STRIDED_SIZES(X)
@@ -314,10 +277,10 @@ bool strided_size_supported(int n) {
 
 int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, float2* out, PassAddr ain, PassAddr aout,
                        int nouter, int ncols, int wcols, const MulArgs& mul, const float2* tw, cudaStream_t st,
-                       float2* const* peers, int npeers) {
+                       float2* const* peers, int npeers, int x_sms) {
   make_fastdiv(ain);
   make_fastdiv(aout);
-  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw, {nullptr}, prefetch_distance(), nouter};
+  StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw, {nullptr}, nouter, x_sms};
   if (peers) {
     if (npeers > SMK_MAX_RANKS) { set_error("too many ranks for the fused exchange"); return SMK_ERR_ARG; }
     for (int i = 0; i < npeers; ++i) p.peer[i] = peers[i];
@@ -442,7 +405,6 @@ struct C2RParams {
   const float2* tw;
   float norm;       // nx*ny*nz as float (the reference divides: box /= NX*NY*NZ)
   double* stats;    // [2] sum, sum of squares (atomically accumulated) or null
-  int pf_dist;      // L2 prefetch distance in tiles (0 = off)
   int discard_in;   // chained mode: the input is an L2-resident scratch slot; drop its lines after reading (no write-back)
 };
 
@@ -457,14 +419,6 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
   //      (descending), both coalesced, and writes Z[k] = A + iB, Z[M-k] = conj(A) + i conj(B) with
   //      A = X[k] + conj(X[M-k]), B = (X[k] - conj(X[M-k])) w^-k.  The imaginary parts of the DC and Nyquist bins
   //      are ignored, as FFTW's / pocketfft's c2r do.
-  if (p.pf_dist > 0) {
-    const long long l0 = ((long long)blockIdx.x + p.pf_dist) * LINES;
-    if (l0 + LINES <= p.nlines) {
-      const char* nxt = reinterpret_cast<const char*>(p.in + l0 * p.pitch);
-      const int nline128 = LINES * p.pitch * 8 / 128;
-      for (int i = threadIdx.x; i < nline128; i += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128LL * i));
-    }
-  }
   constexpr int KI = (M / 2 + 1 + 31) / 32;   // (k, M-k) pairs per lane and line
   for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
     const bool ok = line0 + line < p.nlines;
@@ -595,7 +549,7 @@ static int launch_c2r_t(const C2RParams& p, cudaStream_t st) {
 
 int launch_c2r_z(int NZ, const float2* in, float* out, long long nlines, int pitch, const float2* tw, float norm,
                  double* stats, cudaStream_t st, bool discard_in) {
-  C2RParams p{in, out, nlines, pitch, tw, norm, stats, prefetch_distance() * 2 / 3, discard_in ? 1 : 0};
+  C2RParams p{in, out, nlines, pitch, tw, norm, stats, discard_in ? 1 : 0};
   switch (NZ / 2) {
 #define X(M_) case M_: return launch_c2r_t<M_>(p, st);
     SMK_Z_HALF_SIZES(X)

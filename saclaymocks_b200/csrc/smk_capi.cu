@@ -36,6 +36,7 @@ struct smk_ctx {
   float2* xbuf[4] = {nullptr, nullptr, nullptr, nullptr};
   float2* xpeer[4][SMK_MAX_RANKS] = {};
   bool xconnected[4] = {false, false, false, false};
+  int x_sms = 0;                // persistent fused-exchange x pass on this many CTAs (smk_exchange_set_sms; 0 = off)
   // y<->z chaining through L2 (see chain_setup): planes per group (0 = off), internal streams, ring of scratch slots
   int yz_group = 0, yz_streams = 0;
   bool yz_discard = true;
@@ -468,6 +469,12 @@ int smk_exchange_connect(smk_ctx* c, int buf, const unsigned char* handles) {
   return SMK_OK;
 }
 
+int smk_exchange_set_sms(smk_ctx* c, int nsm) {
+  if (nsm < 0) { set_error("smk_exchange_set_sms: negative CTA count"); return SMK_ERR_ARG; }
+  c->x_sms = nsm;
+  return SMK_OK;
+}
+
 void* smk_exchange_ptr(smk_ctx* c, int buf) { return (buf >= 0 && buf < c->nxbuf) ? c->xbuf[buf] : nullptr; }
 
 int smk_synth_c2r_local_p2p(smk_ctx* c, void* boxk, int product, const float* wtable, int store_p0, double dgrowth0,
@@ -507,7 +514,7 @@ int smk_synth_c2r_local_p2p(smk_ctx* c, void* boxk, int product, const float* wt
   aout.tile_stride = (long long)c->nyl * c->nxl * LX;
   tmark(c, PASS_INV_X);
   int rc = launch_c2c_strided(c->nx, true, mode, (const float2*)boxk, nullptr, ain, aout, c->nyl, c->pitch, c->nzh, m,
-                              c->tw_x, c->stream, peers, c->nranks);
+                              c->tw_x, c->stream, peers, c->nranks, c->x_sms);
   tmark(c, -1);
   return rc;
 }

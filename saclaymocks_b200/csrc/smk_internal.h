@@ -67,7 +67,7 @@ enum MulMode { MUL_NONE = 0, MUL_TABLE = 1, MUL_ETA = 2, MUL_VEL = 3 };
 
 int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, float2* out, PassAddr ain, PassAddr aout,
                        int nouter, int ncols, int wcols, const MulArgs& mul, const float2* tw, cudaStream_t st,
-                       float2* const* peers = nullptr, int npeers = 0);
+                       float2* const* peers = nullptr, int npeers = 0, int x_sms = 0);
 
 int launch_r2c_z(int NZ, const float* in, float2* out, long long nlines, int pitch, const float2* tw,
                  bool philox, uint64_t seed, long long cell0, cudaStream_t st);
@@ -91,7 +91,6 @@ int launch_pk_weights(const PkParams& p, cudaStream_t st);
 int launch_pk_estimate(const float2* boxk, const float* kx, const float* ky, const float* kz, int nx, int nyl, int nzh,
                        int pitch, int y0, int nz, int nbins, double kmin, double kmax, double* out, cudaStream_t st);
 
-int prefetch_distance();
 bool strided_size_supported(int n);
 int strided_tile_width(int n);   // kz columns per tile of the strided pass of length n
 bool z_size_supported(int nz);

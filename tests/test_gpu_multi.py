@@ -1,5 +1,7 @@
 """Multi-GPU parity: the x-slab / y-slab sharded pipeline (all-to-all transposes, halo exchange, skewers sharded by
-owning slab) against the CPU oracle.  Needs >= 2 GPUs (skipped otherwise): run with `gpurun --gpus 2`."""
+owning slab) against the CPU oracle, at 2, 4 and 8 ranks, including the 1024-, 2048- and 2560-point fused-exchange x
+passes of the benched configurations.  A case needs as many GPUs as ranks (skipped otherwise): `gpurun --gpus 8` runs
+all of them; the log of that run is kept under profiles/."""
 import os
 import sys
 
@@ -80,9 +82,19 @@ def _worker(rank, world, port, shape, dcell, out, p2p, xsms=0):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,shape,p2p,xsms", [(2, (32, 32, 96), "auto", 0), (2, (64, 32, 96), "0", 0),
+CASES = [(2, (32, 32, 96), "auto", 0), (2, (64, 32, 96), "0", 0),
                                                   (2, (2048, 32, 96), "1", 0), (4, (64, 64, 96), "auto", 0),
-                                                  (2, (64, 32, 96), "1", 3), (2, (2048, 32, 96), "1", 5)])
+                                                  (2, (64, 32, 96), "1", 3), (2, (2048, 32, 96), "1", 5),
+                                                  # the transform lengths and rank counts bench.py runs (configs 3, 4)
+                                                  (2, (1024, 32, 96), "1", 0), (4, (1024, 32, 96), "1", 0),
+                                                  (4, (2048, 32, 96), "1", 0), (4, (64, 64, 96), "0", 0),
+                                                  (8, (64, 64, 96), "auto", 0), (8, (64, 64, 96), "0", 0),
+                                                  (8, (2048, 64, 96), "1", 0), (8, (2560, 64, 96), "1", 0),
+                                                  (8, (2560, 64, 96), "1", 24)]
+
+
+@pytest.mark.parametrize("world,shape,p2p,xsms", CASES,
+                         ids=["w%d-%dx%dx%d-p2p%s-xsms%d" % (w, s[0], s[1], s[2], p, x) for w, s, p, x in CASES])
 def test_sharded_pipeline_matches_oracle(tmp_path, world, shape, p2p, xsms):
     """p2p: "1" = fused peer-store exchange (tiled receive layout), "0" = NCCL all-to-all, "auto" = by size;
     xsms > 0: the fused x pass runs persistent on that many CTAs (SMK_X_SMS), several tiles per CTA."""
@@ -90,7 +102,7 @@ def test_sharded_pipeline_matches_oracle(tmp_path, world, shape, p2p, xsms):
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     out = str(tmp_path / "res")
-    port = 29600 + world + shape[0] + 7 * xsms
+    port = 29600 + 20 * CASES.index((world, shape, p2p, xsms))
     mp.spawn(_worker, args=(world, port, shape, 3364.0 / shape[2], out, p2p, xsms), nprocs=world, join=True)
     pieces = 0
     for r in range(world):
