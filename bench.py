@@ -381,6 +381,8 @@ def run_gpu(args):
         wall = time.time() - t0
     passes = pipe.bs.timing_collect()
     pipe.bs.timing_enable(False)
+    from saclaymocks_b200 import _lib
+    seg, back, sbox = _lib.skewers_stats() if pipe.gather_events else (0, 0, (0, 0, 0))
     t_gather = float(np.mean([a.elapsed_time(b) for a, b in pipe.gather_events])) if pipe.gather_events else 0.0
     pipe.gather_events = None
     t_box = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)) / args.steps
@@ -522,6 +524,8 @@ def run_gpu(args):
                 "grf_cells_per_s_boxes": cells / (max(box_r) * 1e-3), "box_cells_per_s": 13 * cells / (max(box_r) * 1e-3),
                 "skewer_pixels_per_s": npx / (max(skw_r) * 1e-3), "t_boxes_ms": max(box_r), "t_skewers_ms": max(skw_r),
                 "t_gather_ms": max(gat_r),
+                "gather_staging_rank0": {"segments_of_128_pixels": seg, "handed_back_to_global_memory_kernel": back,
+                                         "box_cells_xyz": list(sbox)},
                 "per_rank": {"t_boxes_ms": box_r, "t_skewers_ms": skw_r, "t_gather_ms": gat_r, "forest_pixels": pix_r,
                              "sightlines": nq_r,
                              "skewer_pixels_max_over_mean": max(pix_r) / (sum(pix_r) / world) if npx else None,

@@ -160,18 +160,29 @@ int smk_make_boxes_host(smk_ctx* ctx, const float* noise_host, uint64_t seed, co
  * Outputs are [nqso][npix] float, written only at the pixels owned by this call: delta_l, eta_par,
  * vpar (before the make_spectra.py:510 rescale); pixels owned but outside the forest get -1e6 / 0 / 0
  * (make_spectra.py:99-101).  Neighbour indices are clamped to the slab (documented deviation: the reference
- * gather is unchecked). */
+ * gather is unchecked).
+ * With a context (ctx != NULL), nz % 4 == 0 and 16-byte aligned fields the gather is staged: every warp brings the
+ * box of cells its 128 pixels can touch into shared memory with 3-D TMA loads (box sized from dir_x_max / dir_y_max);
+ * segments whose windows reach over a box edge, or that are more oblique than the box allows, are handed back to the
+ * global-memory kernel inside the same call. */
 typedef struct smk_geom {
   int nx, ny, nz;       /* full box */
   double dx, dy, dz;    /* cell size */
   double r0;            /* h*R(z0): distance of the box centre */
   int dmax;             /* half width of the Gaussian window in cells (3) */
   double pixel_step;    /* spacing of rvec in Mpc/h (make_spectra.py -pixel, 0.2); 0 = unknown / non-uniform */
+  double dir_x_max;     /* largest |X| / R_QSO and |Y| / R_QSO of the catalogue (direction cosines of the most oblique */
+  double dir_y_max;     /* sightline): sizes the shared-memory box of the staged gather; 0 = unknown (0.25 assumed) */
 } smk_geom;
 
 int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs, double xmin,
                 double xmax, int rsd, int dla, int nqso, const double* qso_xyzr, const int* npix_forest,
                 const double* rvec, int npix, float* delta_l, float* eta_par, float* vpar);
+
+/* How the calling thread's last smk_skewers / smk_skewers_fgpa call ran (synchronises its stream): segments = pieces
+ * of 128 pixels launched (0 when the staged kernel was not used), handed_back = those the staged kernel left to the
+ * global-memory kernel, box = staged box extent in cells (x, y, z).  Any output pointer may be NULL. */
+int smk_skewers_stats(smk_ctx* ctx, long long* segments, long long* handed_back, int box[3]);
 
 /* ---- small-scale field (merge_spectra.py:308-324): delta_s = irfft(rfft(noise) * filt)[:npix] * zscale.
  * noise: [nqso][nfft] float white noise, or NULL to draw Philox(seed, quasar index).  filt_rows: [nrows][nfft/2+1]

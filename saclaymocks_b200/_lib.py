@@ -15,7 +15,7 @@ EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy",
            "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
            "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
            "smk_make_boxes_host", "smk_skewers", "smk_skewers_fgpa", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
-           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light", "smk_exchange_set_sms")
+           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light", "smk_exchange_set_sms", "smk_skewers_stats")
 
 
 class SmkError(RuntimeError):
@@ -24,7 +24,8 @@ class SmkError(RuntimeError):
 
 class Geom(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("dx", C.c_double), ("dy", C.c_double),
-                ("dz", C.c_double), ("r0", C.c_double), ("dmax", C.c_int), ("pixel_step", C.c_double)]
+                ("dz", C.c_double), ("r0", C.c_double), ("dmax", C.c_int), ("pixel_step", C.c_double),
+                ("dir_x_max", C.c_double), ("dir_y_max", C.c_double)]
 
 
 _lib = None
@@ -64,6 +65,7 @@ def lib():
     L.smk_make_boxes_host.argtypes = [vp, vp, u64, C.POINTER(vp), d, C.POINTER(vp), C.POINTER(d)]
     L.smk_skewers.argtypes = [vp, C.POINTER(Geom), C.POINTER(vp), i, i, d, d, i, i, i, vp, vp, vp, i, vp, vp, vp]
     L.smk_skewers_fgpa.argtypes = L.smk_skewers.argtypes + [vp, vp, vp, vp, vp, vp]
+    L.smk_skewers_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(i)]
     L.smk_smallscale.argtypes = [vp, i, i, i, vp, u64, vp, vp, vp, vp, vp, vp]
     L.smk_fgpa.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.smk_pk_weights.argtypes = [vp, vp, vp, i, vp]
@@ -114,6 +116,14 @@ class StreamCtx(object):
             self.close()
         except Exception:
             pass
+
+
+def skewers_stats(ctx=None):
+    """(segments launched by the staged gather, segments handed back to the global-memory kernel, staged box (x, y, z))
+    of this thread's last smk_skewers / smk_skewers_fgpa call."""
+    seg, back, box = C.c_longlong(), C.c_longlong(), (C.c_int * 3)()
+    check(lib().smk_skewers_stats(ctx, C.byref(seg), C.byref(back), box))
+    return int(seg.value), int(back.value), tuple(box)
 
 
 def check(rc):

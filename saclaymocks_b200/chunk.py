@@ -275,7 +275,7 @@ class ChunkPipeline(object):
         fl = (C.c_void_p * 10)()
         for i, k in enumerate(sp.FIELDS):
             fl[i] = self.fields[k].data_ptr()
-        cg = self.geom.c_geom()
+        cg = self.geom.c_geom(c["xyzr"])
         ix0 = self.rank * self.bs.nxl - self.hlo
         nxs = self.bs.nxl + self.hlo + self.hhi
         L = self.bs.lib

@@ -6,8 +6,19 @@
 // eta_par = x_i x_j eta_ij / r^2 and v_par = v.r/|r| contractions.  The 343 reference weights
 // exp(-|dr|^2 / 2 DX^2) factorise as wx*wy*wz, so 21 exponentials are evaluated per pixel instead
 // of 343; sums run in float32 (|error| ~1e-6 of the field rms, far inside the 1e-5 tolerance on F).
+//
+// Two gather kernels share the per-pixel set-up and the epilogue:
+//   * skewers_tma_kernel (default): every warp owns 32*P consecutive pixels of one sightline and brings the box of
+//     cells their windows can touch into shared memory with one 3-D TMA load per field (cp.async.bulk.tensor, one
+//     mbarrier per warp), two fields per stage; all window reads are then shared-memory loads and the z contraction runs
+//     on packed FFMA2 with the horizontal add deferred to the end of the field.
+//   * skewers_multi_kernel: the same arithmetic on global memory through L1 with index clamping -- the path of the
+//     segments the TMA kernel hands back (windows that reach over a box edge, segments too oblique for the staged box).
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "smk_internal.h"
 
@@ -31,8 +42,8 @@ struct SkewerParams {
   const float* delta_s;    // [nqso][npix] or null
   const float *fg_G, *fg_a, *fg_b, *fg_c;   // [npix]
   float* flux;             // [nqso][npix] or null (no epilogue)
-  int pfd;                 // distance (rows of the window) of the L1 row prefetch
-  int pf;                  // tuning bits: 1 = L2 prefetch of the next x slab of the window, 2 = L1 prefetch of the next row, 4 = L1 prefetch of the next x slab
+  int nseg;                // segments of 32*P pixels per sightline (list mode of skewers_multi_kernel, TMA kernel)
+  const int* list;         // skewers_multi_kernel: null = every segment, else [0] = count, [1..] = q * nseg + segment
 };
 
 // Blackwell packed FP32: one FFMA2 / FMUL2 issues two fused multiply-adds (fma.rn.f32x2, sm_100+)
@@ -165,154 +176,14 @@ __global__ void __launch_bounds__(128) skewers_kernel(SkewerParams p, int nchunk
   }
 }
 
-// ---- register-blocked variant: each thread owns P consecutive pixels of one sightline and walks the UNION of
-// their (2*DMAX+1)^3 windows once, so that every field value loaded is used by P pixels.  P consecutive pixels
-// span (P-1)*pixel < one cell, hence the union is at most one cell wider per axis; a pixel's weight is zero outside
-// its own window, which keeps the result identical to the reference's truncated Gaussian sum.
-template <int DMAX, int P, int NF, bool INTERIOR>
-__device__ __forceinline__ void gather_multi(const SkewerParams& p, const float* const (&fp)[NF], int bx, int by,
-                                             int bz, int nxu, int nyu, const int (&dix)[P], const float (&ox)[P],
-                                             const float* wy_s /* [b][q] of this thread, stride 128 */,
-                                             const float (&wz)[P][2 * DMAX + 2], float inv_sig2, float (&acc)[NF][P],
-                                             float (&sx)[P]) {
-  constexpr int WU = 2 * DMAX + 2;
-  const float fdx = (float)p.dx;
-#pragma unroll
-  for (int f = 0; f < NF; ++f)
-#pragma unroll
-    for (int q = 0; q < P; ++q) acc[f][q] = 0.f;
-  int lz[WU];
-#pragma unroll
-  for (int c = 0; c < WU; ++c) lz[c] = INTERIOR ? c : min(max(bz - DMAX + c, 0), p.nz - 1);
-  const int z0 = INTERIOR ? bz - DMAX : 0;      // INTERIOR: the z window [bz-DMAX, bz+DMAX+1] needs no clamping
-#pragma unroll
-  for (int q = 0; q < P; ++q) sx[q] = 0.f;
-  const unsigned plane = (unsigned)p.ny * (unsigned)p.nz;
-  for (int a = 0; a < nxu; ++a) {
-    const int la = INTERIOR ? (bx - DMAX + a - p.ix0) : min(max(bx - DMAX + a - p.ix0, 0), p.nxs - 1);
-    float wxa[P];
-#pragma unroll
-    for (int q = 0; q < P; ++q) {
-      const int m = a - DMAX - dix[q];                      // cell offset from pixel q's own cell
-      const float t = m * fdx + ox[q];
-      wxa[q] = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
-      sx[q] += wxa[q];
-    }
-    for (int b = 0; b < nyu; ++b) {
-      const int lb = INTERIOR ? (by - DMAX + b) : min(max(by - DMAX + b, 0), p.ny - 1);
-      float wab[P];
-#pragma unroll
-      for (int q = 0; q < P; ++q) wab[q] = wxa[q] * wy_s[(b * P + q) * 128];
-      const size_t row = (size_t)la * plane + (unsigned)lb * (unsigned)p.nz + z0;
-#pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        const float* __restrict__ src = fp[f] + row;
-        float r[WU];
-#pragma unroll
-        for (int c = 0; c < WU; ++c) r[c] = __ldg(src + lz[c]);
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-          float s = 0.f;
-#pragma unroll
-          for (int c = 0; c < WU; ++c) s = fmaf(wz[q][c], r[c], s);
-          acc[f][q] = fmaf(wab[q], s, acc[f][q]);
-        }
-      }
-    }
-  }
-}
+// ---- register-blocked gathers: each thread owns P consecutive pixels of one sightline and walks the UNION of their
+// (2*DMAX+1)^3 windows once, so that every field value loaded is used by P pixels.  P consecutive pixels span
+// (P-1)*pixel < one cell, hence the union is at most one cell wider per axis; a pixel's weight is zero outside its
+// own window, which keeps the result identical to the reference's truncated Gaussian sum.
+constexpr int DMAX = 3;
+constexpr int WU = 2 * DMAX + 2;          // union window width (cells)
 
-// Same walk with packed arithmetic: the z contraction runs on pairs of cells (4 FMUL2/FFMA2 + one add per pixel and
-// row instead of 8 FFMA) and the row accumulation on pairs of pixels (P/2 FFMA2 instead of P FFMA): 30 instead of 44
-// issue slots per (row, field) at P = 4.  wz2[q][j] = (wz[q][2j], wz[q][2j+1]); acc2[f][h] = pixels (2h, 2h+1).
-template <int DMAX, int P, int NF, bool INTERIOR>
-__device__ __forceinline__ void gather_multi2(const SkewerParams& p, const float* const (&fp)[NF], int bx, int by,
-                                              int bz, int nxu, int nyu, const int (&dix)[P], const float (&ox)[P],
-                                              const float* wy_s, const float2 (&wz2)[P][DMAX + 1], float inv_sig2,
-                                              float2 (&acc2)[NF][P / 2], float (&sx)[P]) {
-  constexpr int WU = 2 * DMAX + 2;
-  static_assert(P % 2 == 0, "packed gather works on pixel pairs");
-  const float fdx = (float)p.dx;
-#pragma unroll
-  for (int f = 0; f < NF; ++f)
-#pragma unroll
-    for (int h = 0; h < P / 2; ++h) acc2[f][h] = make_float2(0.f, 0.f);
-  int lz[WU];
-#pragma unroll
-  for (int c = 0; c < WU; ++c) lz[c] = INTERIOR ? c : min(max(bz - DMAX + c, 0), p.nz - 1);
-  const int z0 = INTERIOR ? bz - DMAX : 0;
-#pragma unroll
-  for (int q = 0; q < P; ++q) sx[q] = 0.f;
-  const unsigned plane = (unsigned)p.ny * (unsigned)p.nz;
-  for (int a = 0; a < nxu; ++a) {
-    const int la = INTERIOR ? (bx - DMAX + a - p.ix0) : min(max(bx - DMAX + a - p.ix0, 0), p.nxs - 1);
-    if (INTERIOR && (p.pf & 1) && a + 1 < nxu) {
-      // the rows of the next x slab of the window are known now and needed ~8 row iterations from now: pull the
-      // sector at the centre of each into L2 (the loads of a row otherwise expose one DRAM latency per iteration)
-      const size_t nrow = (size_t)(la + 1) * plane + (unsigned)(by - DMAX) * (unsigned)p.nz + z0 + DMAX;
-      for (int b = 0; b < nyu; ++b)
-#pragma unroll
-        for (int f = 0; f < NF; ++f) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp[f] + nrow + (size_t)b * p.nz));
-    }
-    if (INTERIOR && (p.pf & 4) && a + 1 < nxu) {       // same, into L1 (both sectors the window can straddle)
-      const size_t nrow = (size_t)(la + 1) * plane + (unsigned)(by - DMAX) * (unsigned)p.nz + z0;
-      for (int b = 0; b < nyu; ++b)
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow + (size_t)b * p.nz));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow + (size_t)b * p.nz + WU - 1));
-        }
-    }
-    float wxa[P];
-#pragma unroll
-    for (int q = 0; q < P; ++q) {
-      const int m = a - DMAX - dix[q];
-      const float t = m * fdx + ox[q];
-      wxa[q] = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
-      sx[q] += wxa[q];
-    }
-    for (int b = 0; b < nyu; ++b) {
-      const int lb = INTERIOR ? (by - DMAX + b) : min(max(by - DMAX + b, 0), p.ny - 1);
-      if (INTERIOR && (p.pf & 2)) {
-        // L1 prefetch of the window row p.pfd iterations ahead (wrapping into the next x slab)
-        int nb = b + p.pfd, na = a;
-        if (nb >= nyu) { nb -= nyu; ++na; }
-        if (na < nxu) {
-          const size_t nrow = (size_t)(la + (na - a)) * plane + (unsigned)(by - DMAX + nb) * (unsigned)p.nz + z0;
-#pragma unroll
-          for (int f = 0; f < NF; ++f) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(fp[f] + nrow + WU - 1));
-          }
-        }
-      }
-      float2 wab2[P / 2];
-#pragma unroll
-      for (int h = 0; h < P / 2; ++h)
-        wab2[h] = make_float2(wxa[2 * h] * wy_s[(b * P + 2 * h) * 128], wxa[2 * h + 1] * wy_s[(b * P + 2 * h + 1) * 128]);
-      const size_t row = (size_t)la * plane + (unsigned)lb * (unsigned)p.nz + z0;
-#pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        const float* __restrict__ src = fp[f] + row;
-        float2 r2[WU / 2];
-#pragma unroll
-        for (int j = 0; j < WU / 2; ++j) r2[j] = make_float2(__ldg(src + lz[2 * j]), __ldg(src + lz[2 * j + 1]));
-#pragma unroll
-        for (int h = 0; h < P / 2; ++h) {
-          float2 s0 = fmul2(wz2[2 * h][0], r2[0]), s1 = fmul2(wz2[2 * h + 1][0], r2[0]);
-#pragma unroll
-          for (int j = 1; j < WU / 2; ++j) {
-            s0 = ffma2(wz2[2 * h][j], r2[j], s0);
-            s1 = ffma2(wz2[2 * h + 1][j], r2[j], s1);
-          }
-          acc2[f][h] = ffma2(wab2[h], make_float2(s0.x + s0.y, s1.x + s1.y), acc2[f][h]);
-        }
-      }
-    }
-  }
-}
-
-template <int DMAX, int P>
+template <int P>
 __device__ __forceinline__ void pixel_xyz(const SkewerParams& p, int q, int i, double& xv, double& yv, double& zv) {
   const double R = p.qso[4 * q + 3], r = p.rvec[i];
   xv = r * p.qso[4 * q] / R;                 // make_spectra.py:443-452 (same operation order)
@@ -320,28 +191,41 @@ __device__ __forceinline__ void pixel_xyz(const SkewerParams& p, int q, int i, d
   zv = r * p.qso[4 * q + 2] / R;
 }
 
-template <int DMAX, int P, int MINB, bool F2>
-__global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_constant__ SkewerParams p, int nchunk) {
-  constexpr int WU = 2 * DMAX + 2;
-  const int q = blockIdx.x / nchunk;
-  const int i0 = ((blockIdx.x - q * nchunk) * blockDim.x + threadIdx.x) * P;
-  if (i0 >= p.npix) return;
+// Per-thread state of P consecutive pixels: cells, in-cell offsets, the union window and the separable weights along
+// y and z (x weights are re-evaluated inside the walk, one exponential per pixel and window plane).
+template <int P>
+struct PixelGroup {
+  unsigned actmask;            // pixels of this thread that are owned by the slab and inside the forest
+  int bx, by, bz;              // lowest cell of the union of the windows' centres
+  int nxu, nyu;                // union window extent along x / y (7 or 8)
+  int tz;                      // highest centre cell along z
+  int dix[P];                  // centre cell of pixel k minus bx (100 for an inactive pixel: zero weight everywhere)
+  float ox[P];                 // cell centre - pixel along x
+  float wy[P][WU];             // y weights over the union window
+  float2 wz2[P][WU / 2];       // z weights over the union window, packed in pairs of cells
+  float syz[P];                // (sum of y weights) * (sum of z weights)
+};
+
+// Set-up of make_spectra.py:47-62 for the P pixels starting at i0 of sightline q.  Writes the sentinels of
+// make_spectra.py:99-101 for owned pixels beyond the forest.  Returns false when no pixel is left to gather.
+template <int P>
+__device__ __forceinline__ bool pixel_group_setup(const SkewerParams& p, int q, int i0, PixelGroup<P>& g) {
   const int nfor = p.npix_forest[q];
   const double LX = p.dx * p.nx, LY = p.dy * p.ny, LZ = p.dz * p.nz;
   const float inv_sig2 = (float)(1.0 / (2.0 * p.dx * p.dx));
-  const float fdz = (float)p.dz;
-  unsigned actmask = 0;
+  const float fdy = (float)p.dy, fdz = (float)p.dz;
+  g.actmask = 0;
   int ix[P], iy[P], iz[P];
-  float ox[P], oy[P], oz[P];
+  float oy[P], oz[P];
   int bx = 1 << 30, by = 1 << 30, bz = 1 << 30, tx = -(1 << 30), ty = -(1 << 30), tz = -(1 << 30);
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     const int i = i0 + k;
     ix[k] = iy[k] = iz[k] = 0;
-    ox[k] = oy[k] = oz[k] = 0.f;
+    g.ox[k] = oy[k] = oz[k] = 0.f;
     if (i >= p.npix) continue;
     double xv, yv, zv;
-    pixel_xyz<DMAX, P>(p, q, i, xv, yv, zv);
+    pixel_xyz<P>(p, q, i, xv, yv, zv);
     if (!(xv > p.xmin) || !(xv <= p.xmax)) continue;            // owned by another slab
     if (i >= nfor) {                                            // make_spectra.py:99-101
       const size_t o = (size_t)q * p.npix + i;
@@ -354,181 +238,519 @@ __global__ void __launch_bounds__(128, MINB) skewers_multi_kernel(const __grid_c
     ix[k] = (int)((xv + LX / 2) / p.dx);                        // make_spectra.py:47-49
     iy[k] = (int)((yv + LY / 2) / p.dy);
     iz[k] = (int)((zv + LZ / 2 - p.r0) / p.dz);
-    ox[k] = (float)((ix[k] + 0.5) * p.dx - LX / 2 - xv);        // cell centre - pixel, make_spectra.py:54-56
+    g.ox[k] = (float)((ix[k] + 0.5) * p.dx - LX / 2 - xv);      // cell centre - pixel, make_spectra.py:54-56
     oy[k] = (float)((iy[k] + 0.5) * p.dy - LY / 2 - yv);
     oz[k] = (float)((iz[k] + 0.5) * p.dz - LZ / 2 + p.r0 - zv);
-    actmask |= 1u << k;
+    g.actmask |= 1u << k;
     bx = min(bx, ix[k]); by = min(by, iy[k]); bz = min(bz, iz[k]);
     tx = max(tx, ix[k]); ty = max(ty, iy[k]); tz = max(tz, iz[k]);
   }
-  if (!actmask) return;
+  if (!g.actmask) return false;
   // the host guarantees (P-1)*pixel < cell size, so tx-bx, ty-by, tz-bz are 0 or 1
-  const int nxu = 2 * DMAX + 1 + (tx - bx), nyu = 2 * DMAX + 1 + (ty - by);
-  int dix[P], diy[P];
-  float wz[P][WU], sz[P];
+  g.bx = bx; g.by = by; g.bz = bz; g.tz = tz;
+  g.nxu = 2 * DMAX + 1 + (tx - bx);
+  g.nyu = 2 * DMAX + 1 + (ty - by);
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    const bool act = (actmask >> k) & 1;
-    dix[k] = act ? ix[k] - bx : 100;      // an inactive pixel gets zero weight everywhere
-    diy[k] = iy[k] - by;
-    sz[k] = 0.f;
+    const bool act = (g.actmask >> k) & 1;
+    g.dix[k] = act ? ix[k] - bx : 100;      // an inactive pixel gets zero weight everywhere
+    const int diy = iy[k] - by, diz = iz[k] - bz;
+    float sy = 0.f, sz = 0.f;
+    float wz[WU];
 #pragma unroll
     for (int c = 0; c < WU; ++c) {
-      const int m = c - DMAX - (iz[k] - bz);
-      const float t = m * fdz + oz[k];
-      wz[k][c] = (act && m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
-      sz[k] += wz[k][c];
+      const int mz = c - DMAX - diz, my = c - DMAX - diy;
+      const float tzz = mz * fdz + oz[k], tyy = my * fdy + oy[k];
+      wz[c] = (act && mz >= -DMAX && mz <= DMAX) ? __expf(-tzz * tzz * inv_sig2) : 0.f;
+      g.wy[k][c] = (act && my >= -DMAX && my <= DMAX) ? __expf(-tyy * tyy * inv_sig2) : 0.f;
+      sz += wz[c];
+      sy += g.wy[k][c];
     }
+#pragma unroll
+    for (int j = 0; j < WU / 2; ++j) g.wz2[k][j] = make_float2(wz[2 * j], wz[2 * j + 1]);
+    g.syz[k] = sy * sz;
   }
-  float2 wz2[P][DMAX + 1];      // packed copy for the FFMA2 path (dead code otherwise)
-#pragma unroll
-  for (int k = 0; k < P; ++k)
-#pragma unroll
-    for (int j = 0; j <= DMAX; ++j) wz2[k][j] = make_float2(wz[k][2 * j], wz[k][2 * j + 1]);
-  // y weights of the union window, once per thread, shared by the two field-group passes: [b][q][thread]
-  __shared__ float s_wy[(2 * DMAX + 2) * P * 128];
-  float* wy_s = s_wy + threadIdx.x;
-  float sy[P];
-  {
-    const float fdy = (float)p.dy;
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-      sy[k] = 0.f;
-#pragma unroll
-      for (int b = 0; b < WU; ++b) {
-        const int m = b - DMAX - diy[k];
-        const float t = m * fdy + oy[k];
-        const float w = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
-        wy_s[(b * P + k) * 128] = w;
-        sy[k] += w;
-      }
-    }
-  }
-  // whole union window inside the slab: no index clamping, z offsets become immediates
-  const bool interior = bx - DMAX - p.ix0 >= 0 && bx - DMAX - p.ix0 + nxu <= p.nxs && by - DMAX >= 0 &&
-                        by - DMAX + nyu <= p.ny && bz - DMAX >= 0 && bz + DMAX + 1 < p.nz;
-  float sx[P];
-  const int NFI = p.rsd ? (p.dla ? 10 : 7) : 1;
-  float d0[P], inv_sw[P];
+  return true;
+}
+
+// whole union window inside the slab (no index clamping needed)
+template <int P>
+__device__ __forceinline__ bool group_interior(const SkewerParams& p, const PixelGroup<P>& g) {
+  return g.bx - DMAX - p.ix0 >= 0 && g.bx - DMAX - p.ix0 + g.nxu <= p.nxs && g.by - DMAX >= 0 &&
+         g.by - DMAX + g.nyu <= p.ny && g.bz - DMAX >= 0 && g.tz + DMAX < p.nz;
+}
+
+// Running results of a pixel group: fields arrive in the order delta, eta_xx, eta_yy, eta_zz, eta_xy, eta_xz, eta_yz,
+// vx, vy, vz and are contracted on the fly (make_spectra.py:116-127), float64 like the reference's x*eta*x products.
+template <int P>
+struct PixelResult {
+  float d0[P];
   double eta[P], vel[P];
-#pragma unroll
-  for (int k = 0; k < P; ++k) { eta[k] = 0.0; vel[k] = 0.0; }
-#define SMK_GATHER(NF_, ACC, SX, SY_UNUSED)                                                                              \
-  if constexpr (F2) {                                                                                                    \
-    float2 acc2_[NF_][P / 2];                                                                                            \
-    if (interior) gather_multi2<DMAX, P, NF_, true>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz2, inv_sig2, acc2_, SX); \
-    else gather_multi2<DMAX, P, NF_, false>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz2, inv_sig2, acc2_, SX);       \
-    _Pragma("unroll") for (int f_ = 0; f_ < NF_; ++f_)                                                                   \
-      _Pragma("unroll") for (int h_ = 0; h_ < P / 2; ++h_) {                                                             \
-        ACC[f_][2 * h_] = acc2_[f_][h_].x;                                                                               \
-        ACC[f_][2 * h_ + 1] = acc2_[f_][h_].y;                                                                           \
-      }                                                                                                                  \
-  } else {                                                                                                               \
-    if (interior) gather_multi<DMAX, P, NF_, true>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz, inv_sig2, ACC, SX);  \
-    else gather_multi<DMAX, P, NF_, false>(p, fp, bx, by, bz, nxu, nyu, dix, ox, wy_s, wz, inv_sig2, ACC, SX);          \
+};
+
+template <int P>
+__device__ __forceinline__ void result_add(PixelResult<P>& r, int f, int k, float val, double xv, double yv, double zv) {
+  switch (f) {
+    case 0: r.d0[k] = val; break;
+    case 1: r.eta[k] += xv * (double)val * xv; break;
+    case 2: r.eta[k] += yv * (double)val * yv; break;
+    case 3: r.eta[k] += zv * (double)val * zv; break;
+    case 4: r.eta[k] += 2 * xv * (double)val * yv; break;
+    case 5: r.eta[k] += 2 * xv * (double)val * zv; break;
+    case 6: r.eta[k] += 2 * yv * (double)val * zv; break;
+    case 7: r.vel[k] += (double)val * xv; break;
+    case 8: r.vel[k] += (double)val * yv; break;
+    default: r.vel[k] += (double)val * zv; break;
   }
-  if (NFI == 1) {
-    float acc[1][P];
-    const float* const fp[1] = {p.f[0]};
-    SMK_GATHER(1, acc, sx, 0)
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-      inv_sw[k] = ((actmask >> k) & 1) ? 1.0f / (sx[k] * sy[k] * sz[k]) : 0.f;
-      d0[k] = acc[0][k];
-    }
-  } else {
-    {   // group A: delta, eta_xx, eta_yy, eta_zz, eta_xy
-      float acc[5][P];
-      const float* const fp[5] = {p.f[0], p.f[1], p.f[2], p.f[3], p.f[4]};
-      SMK_GATHER(5, acc, sx, 0)
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        inv_sw[k] = ((actmask >> k) & 1) ? 1.0f / (sx[k] * sy[k] * sz[k]) : 0.f;
-        d0[k] = acc[0][k];
-        double xv, yv, zv;
-        pixel_xyz<DMAX, P>(p, q, min(i0 + k, p.npix - 1), xv, yv, zv);
-        eta[k] = xv * (double)(acc[1][k] * inv_sw[k]) * xv + yv * (double)(acc[2][k] * inv_sw[k]) * yv +
-                 zv * (double)(acc[3][k] * inv_sw[k]) * zv + 2 * xv * (double)(acc[4][k] * inv_sw[k]) * yv;
-      }
-    }
-    float sx2[P];
-    if (NFI == 10) {   // group B: eta_xz, eta_yz, vx, vy, vz
-      float acc[5][P];
-      const float* const fp[5] = {p.f[5], p.f[6], p.f[7], p.f[8], p.f[9]};
-      SMK_GATHER(5, acc, sx2, 0)
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        double xv, yv, zv;
-        pixel_xyz<DMAX, P>(p, q, min(i0 + k, p.npix - 1), xv, yv, zv);
-        eta[k] += 2 * xv * (double)(acc[0][k] * inv_sw[k]) * zv + 2 * yv * (double)(acc[1][k] * inv_sw[k]) * zv;
-        vel[k] = (double)(acc[2][k] * inv_sw[k]) * xv + (double)(acc[3][k] * inv_sw[k]) * yv +
-                 (double)(acc[4][k] * inv_sw[k]) * zv;
-      }
-    } else {           // group B': eta_xz, eta_yz
-      float acc[2][P];
-      const float* const fp[2] = {p.f[5], p.f[6]};
-      SMK_GATHER(2, acc, sx2, 0)
-#pragma unroll
-      for (int k = 0; k < P; ++k) {
-        double xv, yv, zv;
-        pixel_xyz<DMAX, P>(p, q, min(i0 + k, p.npix - 1), xv, yv, zv);
-        eta[k] += 2 * xv * (double)(acc[0][k] * inv_sw[k]) * zv + 2 * yv * (double)(acc[1][k] * inv_sw[k]) * zv;
-      }
-    }
-  }
-#undef SMK_GATHER
+}
+
+template <int P>
+__device__ __forceinline__ void result_store(const SkewerParams& p, int q, int i0, unsigned actmask, int nf,
+                                             const PixelResult<P>& r) {
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     if (!((actmask >> k) & 1)) continue;
     const size_t o = (size_t)q * p.npix + i0 + k;
     double xv, yv, zv;
-    pixel_xyz<DMAX, P>(p, q, i0 + k, xv, yv, zv);
+    pixel_xyz<P>(p, q, i0 + k, xv, yv, zv);
     const double RR = xv * xv + yv * yv + zv * zv;
-    const float dl = d0[k] * inv_sw[k];
-    const float ep = NFI >= 7 ? (float)(eta[k] / RR) : 0.f;
+    const float dl = r.d0[k];
+    const float ep = nf >= 7 ? (float)(r.eta[k] / RR) : 0.f;
     p.delta_l[o] = dl;
     if (p.eta_par) p.eta_par[o] = ep;
-    if (p.vpar) p.vpar[o] = NFI == 10 ? (float)(vel[k] / sqrt(RR)) : 0.f;
+    if (p.vpar) p.vpar[o] = nf == 10 ? (float)(r.vel[k] / sqrt(RR)) : 0.f;
     if (p.flux) store_flux(p, o, i0 + k, dl, ep);
   }
 }
 
-template <int P, int MINB, bool F2 = false>
-static int launch_multi(const SkewerParams& p, cudaStream_t st) {
-  const int NT = 128;
-  int nchunk = (p.npix + NT * P - 1) / (NT * P);
-  long long nblocks = (long long)nchunk * p.nqso;
-  if (nblocks > 2147483647LL) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
-  skewers_multi_kernel<3, P, MINB, F2><<<(unsigned)nblocks, NT, 0, st>>>(p, nchunk);
+// One walk over the union window for NF fields; src(f, a, b) returns the address of the 8 consecutive z cells of
+// window row (a, b) of field f.  z contraction on pairs of cells (4 FMUL2/FFMA2 per pixel and row), row accumulation
+// with the packed weight (wab, wab): the two halves of acc2 are added only at the end of the walk.
+template <int P, int NF, bool SUMX, class Src>
+__device__ __forceinline__ void walk_window(const SkewerParams& p, const PixelGroup<P>& g, int nxu, int nyu, Src src,
+                                            float2 (&acc2)[NF][P], float (&sx)[P]) {
+  const float fdx = (float)p.dx;
+  const float inv_sig2 = (float)(1.0 / (2.0 * p.dx * p.dx));
+#pragma unroll
+  for (int f = 0; f < NF; ++f)
+#pragma unroll
+    for (int k = 0; k < P; ++k) acc2[f][k] = make_float2(0.f, 0.f);
+  if (SUMX) {
+#pragma unroll
+    for (int k = 0; k < P; ++k) sx[k] = 0.f;
+  }
+#pragma unroll 1
+  for (int a = 0; a < nxu; ++a) {
+    float wxa[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const int m = a - DMAX - g.dix[k];                      // cell offset from pixel k's own cell
+      const float t = m * fdx + g.ox[k];
+      wxa[k] = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
+      if (SUMX) sx[k] += wxa[k];
+    }
+#pragma unroll
+    for (int b = 0; b < WU; ++b) {
+      if (b < nyu) {
+        float2 wab[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const float w = wxa[k] * g.wy[k][b];
+          wab[k] = make_float2(w, w);
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          const float* __restrict__ row = src(f, a, b);
+          float2 r2[WU / 2];
+#pragma unroll
+          for (int j = 0; j < WU / 2; ++j) r2[j] = make_float2(row[2 * j], row[2 * j + 1]);
+#pragma unroll
+          for (int k = 0; k < P; ++k) {
+            float2 s2 = fmul2(g.wz2[k][0], r2[0]);
+#pragma unroll
+            for (int j = 1; j < WU / 2; ++j) s2 = ffma2(g.wz2[k][j], r2[j], s2);
+            acc2[f][k] = ffma2(wab[k], s2, acc2[f][k]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// fold the NF fields [f0, f0+NF) of one walk into the running results
+template <int P, int NF>
+__device__ __forceinline__ void fold_fields(const SkewerParams& p, int q, int i0, int f0, const float2 (&acc2)[NF][P],
+                                            const float (&inv_sw)[P], PixelResult<P>& r) {
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    double xv, yv, zv;
+    pixel_xyz<P>(p, q, min(i0 + k, p.npix - 1), xv, yv, zv);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) result_add<P>(r, f0 + f, k, (acc2[f][k].x + acc2[f][k].y) * inv_sw[k], xv, yv, zv);
+  }
+}
+
+// ---------------------------------------------------------------- global-memory walk (clamped indices)
+// All segments (list == null: one CTA per 4 segments of a sightline) or the segments the TMA kernel handed back
+// (list mode: a fixed grid walks list[1 .. list[0]]).
+template <int P>
+__device__ __forceinline__ void global_segment(const SkewerParams& p, int q, int seg) {
+  const int lane = threadIdx.x & 31;
+  const int i0 = (seg * 32 + lane) * P;
+  if (i0 >= p.npix) return;
+  PixelGroup<P> g;
+  if (!pixel_group_setup<P>(p, q, i0, g)) return;
+  const int nf = p.rsd ? (p.dla ? 10 : 7) : 1;
+  const bool interior = group_interior<P>(p, g);
+  const unsigned plane = (unsigned)p.ny * (unsigned)p.nz;
+  PixelResult<P> r;
+  float inv_sw[P], sx[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) { r.d0[k] = 0.f; r.eta[k] = 0.0; r.vel[k] = 0.0; inv_sw[k] = 0.f; }
+  // rows are fetched through L1; a window that reaches over the slab gets its indices clamped (documented deviation
+  // from the reference's unchecked gather, include/smk.h), and its 8 z cells are staged in a local array
+  auto run = [&](auto nfc, int f0, auto sumx) {
+    constexpr int NF = decltype(nfc)::value;
+    constexpr bool SUMX = decltype(sumx)::value;
+    float2 acc2[NF][P];
+    if (interior) {
+      const float* base[NF];
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+        base[f] = p.f[f0 + f] + ((size_t)(g.bx - DMAX - p.ix0) * plane + (unsigned)(g.by - DMAX) * (unsigned)p.nz + (g.bz - DMAX));
+      walk_window<P, NF, SUMX>(p, g, g.nxu, g.nyu,
+                               [&](int f, int a, int b) { return base[f] + ((size_t)a * plane + (unsigned)b * (unsigned)p.nz); },
+                               acc2, sx);
+    } else {
+      // clamped walk: one row at a time into registers (rare: only at the edges of the box)
+      const float fdx = (float)p.dx;
+      const float inv_sig2 = (float)(1.0 / (2.0 * p.dx * p.dx));
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int k = 0; k < P; ++k) acc2[f][k] = make_float2(0.f, 0.f);
+      if (SUMX) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) sx[k] = 0.f;
+      }
+      int lz[WU];
+#pragma unroll
+      for (int c = 0; c < WU; ++c) lz[c] = min(max(g.bz - DMAX + c, 0), p.nz - 1);
+      for (int a = 0; a < g.nxu; ++a) {
+        const int la = min(max(g.bx - DMAX + a - p.ix0, 0), p.nxs - 1);
+        float wxa[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const int m = a - DMAX - g.dix[k];
+          const float t = m * fdx + g.ox[k];
+          wxa[k] = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
+          if (SUMX) sx[k] += wxa[k];
+        }
+        for (int b = 0; b < g.nyu; ++b) {
+          const int lb = min(max(g.by - DMAX + b, 0), p.ny - 1);
+          const size_t rowo = (size_t)la * plane + (unsigned)lb * (unsigned)p.nz;
+#pragma unroll
+          for (int f = 0; f < NF; ++f) {
+            const float* __restrict__ srcf = p.f[f0 + f] + rowo;
+            float2 r2[WU / 2];
+#pragma unroll
+            for (int j = 0; j < WU / 2; ++j) r2[j] = make_float2(__ldg(srcf + lz[2 * j]), __ldg(srcf + lz[2 * j + 1]));
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+              // y weights by dynamic index: select with a compile-time unrolled chain
+              float wyb = 0.f;
+#pragma unroll
+              for (int bb = 0; bb < WU; ++bb) wyb = (bb == b) ? g.wy[k][bb] : wyb;
+              const float w = wxa[k] * wyb;
+              float2 s2 = fmul2(g.wz2[k][0], r2[0]);
+#pragma unroll
+              for (int j = 1; j < WU / 2; ++j) s2 = ffma2(g.wz2[k][j], r2[j], s2);
+              acc2[f][k] = ffma2(make_float2(w, w), s2, acc2[f][k]);
+            }
+          }
+        }
+      }
+    }
+    if (SUMX) {
+#pragma unroll
+      for (int k = 0; k < P; ++k) inv_sw[k] = ((g.actmask >> k) & 1) ? 1.0f / (sx[k] * g.syz[k]) : 0.f;
+    }
+    fold_fields<P, NF>(p, q, i0, f0, acc2, inv_sw, r);
+  };
+  using I1 = std::integral_constant<int, 1>;
+  using I2 = std::integral_constant<int, 2>;
+  using T = std::true_type;
+  using F = std::false_type;
+  if (nf == 1) {
+    run(I1{}, 0, T{});
+  } else {
+    run(I2{}, 0, T{});
+    run(I2{}, 2, F{});
+    run(I2{}, 4, F{});
+    if (nf == 10) {
+      run(I2{}, 6, F{});
+      run(I2{}, 8, F{});
+    } else {
+      run(I1{}, 6, F{});
+    }
+  }
+  result_store<P>(p, q, i0, g.actmask, nf, r);
+}
+
+template <int P>
+__global__ void __launch_bounds__(128, 3) skewers_multi_kernel(const __grid_constant__ SkewerParams p) {
+  const int warp = threadIdx.x >> 5;
+  if (p.list == nullptr) {
+    const long long s = (long long)blockIdx.x * 4 + warp;
+    if (s >= (long long)p.nqso * p.nseg) return;
+    const int q = (int)(s / p.nseg);
+    global_segment<P>(p, q, (int)(s - (long long)q * p.nseg));
+  } else {
+    const int n = p.list[0];
+#pragma unroll 1
+    for (int e = blockIdx.x * 4 + warp; e < n; e += gridDim.x * 4) {
+      const int s = p.list[1 + e];
+      const int q = s / p.nseg;
+      global_segment<P>(p, q, s - q * p.nseg);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- staged walk: TMA box loads into shared memory
+struct alignas(64) SkewerTmaParams {
+  CUtensorMap map[10];     // one 3-D tiled map per field: dims (z, y, x-planes of the slab), box (zl, yw, xw)
+  SkewerParams p;
+  int xw, yw, zl;          // box extent in cells
+  int box_elems;           // floats per staged box (xw * yw * zl rounded up to 128 B)
+  int* handback;           // [0] = count, [1..] = q * nseg + segment of the segments left to skewers_multi_kernel
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 3-D box load: coordinates (z, y, x) in elements, any alignment; out-of-range elements arrive as zeros
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+// NW warps per CTA, each on its own segment of 32*P pixels with its own box and mbarrier (no CTA-wide barrier after
+// the set-up); NFG fields staged and walked together.
+template <int P, int NFG, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) skewers_tma_kernel(const __grid_constant__ SkewerTmaParams t) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const SkewerParams& p = t.p;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* const box = reinterpret_cast<float*>(smraw) + (size_t)warp * NFG * t.box_elems;
+  const uint32_t bar = smem_u32(smraw + (size_t)NW * NFG * t.box_elems * sizeof(float)) + 8u * warp;
+  if (lane == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const long long s = (long long)blockIdx.x * NW + warp;
+  if (s >= (long long)p.nqso * p.nseg) return;
+  const int q = (int)(s / p.nseg), seg = (int)(s - (long long)q * p.nseg);
+  const int i0 = (seg * 32 + lane) * P;
+  PixelGroup<P> g;
+  const bool act = (i0 < p.npix) && pixel_group_setup<P>(p, q, i0, g);
+  if (!__any_sync(0xffffffffu, act)) return;
+  if (!act) {                       // idle lane of a live warp: zero weights, window at the box origin
+    g.actmask = 0;
+    g.nxu = g.nyu = 2 * DMAX + 1;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      g.dix[k] = 100; g.ox[k] = 0.f; g.syz[k] = 1.f;
+#pragma unroll
+      for (int c = 0; c < WU; ++c) g.wy[k][c] = 0.f;
+#pragma unroll
+      for (int j = 0; j < WU / 2; ++j) g.wz2[k][j] = make_float2(0.f, 0.f);
+    }
+  }
+  // the box of the warp: lowest window corner of any live lane; every live lane's 8 x 8 x 8 read must fit into it and
+  // every window must lie inside the slab (TMA fills what is outside the tensor with zeros, which only ever meet the
+  // zero weights of the 8th row / plane / cell)
+  const int BIG = 1 << 30;
+  const int x0 = __reduce_min_sync(0xffffffffu, act ? g.bx : BIG), x1 = __reduce_max_sync(0xffffffffu, act ? g.bx : -BIG);
+  const int y0 = __reduce_min_sync(0xffffffffu, act ? g.by : BIG), y1 = __reduce_max_sync(0xffffffffu, act ? g.by : -BIG);
+  const int z0 = __reduce_min_sync(0xffffffffu, act ? g.bz : BIG), z1 = __reduce_max_sync(0xffffffffu, act ? g.bz : -BIG);
+  const bool fits = (x1 - x0 + WU <= t.xw) && (y1 - y0 + WU <= t.yw) && (z1 - z0 + WU <= t.zl);
+  const bool inside = __all_sync(0xffffffffu, !act || group_interior<P>(p, g));
+  if (!fits || !inside) {           // hand the segment back to the global-memory kernel
+    if (lane == 0) t.handback[1 + atomicAdd(t.handback, 1)] = (int)s;
+    return;
+  }
+  const int nxu = __reduce_max_sync(0xffffffffu, g.nxu), nyu = __reduce_max_sync(0xffffffffu, g.nyu);
+  const int ywzl = t.yw * t.zl;
+  const int rowbase = act ? ((g.bx - x0) * t.yw + (g.by - y0)) * t.zl + (g.bz - z0) : 0;
+  const int nf = p.rsd ? (p.dla ? 10 : 7) : 1;
+  PixelResult<P> r;
+  float inv_sw[P], sx[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) { r.d0[k] = 0.f; r.eta[k] = 0.0; r.vel[k] = 0.0; inv_sw[k] = 0.f; }
+  uint32_t parity = 0;
+  const uint32_t box_bytes = (uint32_t)(t.xw * t.yw * t.zl) * (uint32_t)sizeof(float);
+  const float* const mine = box + rowbase;
+  auto stage = [&](auto nfc, int f0, auto sumx) {
+    constexpr int NF = decltype(nfc)::value;
+    constexpr bool SUMX = decltype(sumx)::value;
+    if (lane == 0) {
+      mbar_expect_tx(bar, NF * box_bytes);
+#pragma unroll
+      for (int f = 0; f < NF; ++f)
+        tma_load_3d(smem_u32(box + (size_t)f * t.box_elems), &t.map[f0 + f], z0 - DMAX, y0 - DMAX, x0 - DMAX - p.ix0, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    float2 acc2[NF][P];
+    walk_window<P, NF, SUMX>(p, g, nxu, nyu,
+                             [&](int f, int a, int b) { return mine + (f * t.box_elems + a * ywzl + b * t.zl); }, acc2, sx);
+    __syncwarp();                   // every lane is done with the boxes before the next stage overwrites them
+    if (SUMX) {
+#pragma unroll
+      for (int k = 0; k < P; ++k) inv_sw[k] = ((g.actmask >> k) & 1) ? 1.0f / (sx[k] * g.syz[k]) : 0.f;
+    }
+    if (act) fold_fields<P, NF>(p, q, i0, f0, acc2, inv_sw, r);
+  };
+  using I1 = std::integral_constant<int, 1>;
+  using I2 = std::integral_constant<int, 2>;
+  using T = std::true_type;
+  using F = std::false_type;
+  static_assert(NFG == 2, "stages of two fields");
+  if (nf == 1) {
+    stage(I1{}, 0, T{});
+  } else {
+    stage(I2{}, 0, T{});
+    stage(I2{}, 2, F{});
+    stage(I2{}, 4, F{});
+    if (nf == 10) {
+      stage(I2{}, 6, F{});
+      stage(I2{}, 8, F{});
+    } else {
+      stage(I1{}, 6, F{});
+    }
+  }
+  if (act) result_store<P>(p, q, i0, g.actmask, nf, r);
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (libsmk.so does not link libcuda)
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+constexpr int SKEW_P = 4, SKEW_NFG = 2, SKEW_NW = 4, SKEW_MINB = 3;
+
+// bookkeeping of the calling thread's last gather (smk_skewers_stats)
+struct LastGather { const int* handback = nullptr; long long nsegs = 0; int xw = 0, yw = 0, zl = 0; cudaStream_t st = nullptr; };
+static thread_local LastGather g_last;
+constexpr int SKEW_BOX_MAX = 16;          // largest staged box extent along x / y (cells)
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Staged launch.  Returns SMK_ERR_UNSUPPORTED (without touching the error string) when the inputs do not meet TMA's
+// alignment rules, in which case the caller uses the global-memory kernel for everything.
+static int launch_staged(smk_ctx* ctx, const smk_geom* g, const SkewerParams& p, cudaStream_t st) {
+  EncodeTiledFn encode = encode_tiled_fn();
+  const int nf = p.rsd ? (p.dla ? 10 : 7) : 1;
+  if (!encode || p.nz % 4 != 0) return SMK_ERR_UNSUPPORTED;
+  for (int f = 0; f < nf; ++f)
+    if ((uintptr_t)p.f[f] & 15) return SMK_ERR_UNSUPPORTED;
+  SkewerTmaParams t{};
+  t.p = p;
+  // extent of the box a segment of 32*P pixels can need: cells crossed along the axis + the 8-cell union window
+  const double lseg = (32 * SKEW_P - 1) * g->pixel_step;
+  auto extent = [&](double dir, double d) { return (int)floor(lseg * fmin(fabs(dir), 1.0) / d) + 1 + WU; };
+  const double dirx = g->dir_x_max > 0 ? g->dir_x_max : 0.25, diry = g->dir_y_max > 0 ? g->dir_y_max : 0.25;
+  t.xw = extent(dirx, g->dx) < SKEW_BOX_MAX ? extent(dirx, g->dx) : SKEW_BOX_MAX;
+  t.yw = extent(diry, g->dy) < SKEW_BOX_MAX ? extent(diry, g->dy) : SKEW_BOX_MAX;
+  t.zl = round_up(extent(1.0, g->dz), 4);                        // rows of whole 16-byte units
+  if (t.xw > p.nxs + 2 * DMAX + 2 || t.zl > 256) return SMK_ERR_UNSUPPORTED;
+  t.box_elems = round_up(t.xw * t.yw * t.zl, 32);
+  for (int f = 0; f < nf; ++f) {
+    const cuuint64_t dims[3] = {(cuuint64_t)p.nz, (cuuint64_t)p.ny, (cuuint64_t)p.nxs};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.nz * sizeof(float), (cuuint64_t)p.nz * p.ny * sizeof(float)};
+    const cuuint32_t boxd[3] = {(cuuint32_t)t.zl, (cuuint32_t)t.yw, (cuuint32_t)t.xw};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = encode(&t.map[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.f[f], dims, strides, boxd, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return SMK_ERR_UNSUPPORTED;
+  }
+  const long long nsegs = (long long)p.nqso * p.nseg;
+  if (nsegs > 2147483647LL / 2) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
+  t.handback = (int*)smk_ctx_scratch(ctx, (size_t)(nsegs + 1) * sizeof(int));
+  if (!t.handback) return SMK_ERR_CUDA;
+  SMK_CUDA_OK(cudaMemsetAsync(t.handback, 0, sizeof(int), st));
+  auto kern = skewers_tma_kernel<SKEW_P, SKEW_NFG, SKEW_NW, SKEW_MINB>;
+  const size_t smem = (size_t)SKEW_NW * SKEW_NFG * t.box_elems * sizeof(float) + SKEW_NW * 8;
+  if (smem > 227 * 1024) return SMK_ERR_UNSUPPORTED;
+  SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)((nsegs + SKEW_NW - 1) / SKEW_NW), SKEW_NW * 32, smem, st>>>(t);
+  SMK_CUDA_OK(cudaGetLastError());
+  g_last.handback = t.handback; g_last.nsegs = nsegs; g_last.xw = t.xw; g_last.yw = t.yw; g_last.zl = t.zl; g_last.st = st;
+  // the segments handed back (box edges, oblique segments): fixed grid over the list
+  SkewerParams pl = p;
+  pl.list = t.handback;
+  skewers_multi_kernel<SKEW_P><<<148 * 3, 128, 0, st>>>(pl);
   SMK_CUDA_OK(cudaGetLastError());
   return SMK_OK;
 }
 
-// *fused (if given) tells whether the kernel that ran has the FGPA epilogue (the register-blocked one has)
-int launch_skewers(const SkewerParams& p, int dmax, double pixel_step, cudaStream_t st, bool* fused = nullptr) {
+// *fused (if given) tells whether the kernel that ran has the FGPA epilogue (the register-blocked ones have)
+int launch_skewers(smk_ctx* ctx, const smk_geom* g, SkewerParams& p, int dmax, double pixel_step, bool staged,
+                   cudaStream_t st, bool* fused = nullptr) {
   if (fused) *fused = false;
+  g_last = LastGather();
   if (p.nqso == 0 || p.npix == 0) return SMK_OK;
   const int NT = 128;
-  // register-blocked kernel: valid while P consecutive pixels cannot cross two cell boundaries on any axis
+  // register-blocked kernels: valid while P consecutive pixels cannot cross two cell boundaries on any axis
   const double cell = fmin(p.dx, fmin(p.dy, p.dz));
-  // default: 4 pixels per thread, packed FFMA2 arithmetic, 3 CTAs per SM (measured on B200 at 512 x 512 x 1536, whole
-  // skewer stage: plain FFMA 18.4 ms, FFMA2 17.6-17.8 ms, FFMA2 + L1 prefetch of the next row 16.6 ms)
-  int variant = 42;
-  const char* env = getenv("SMK_SKEW_VARIANT");      // tuning knob: pixels per thread (2, 3, 4), 44 (4 px, 4 CTAs/SM),
-                                                     // 42 / 442 (4 px, FFMA2 arithmetic, 3 / 4 CTAs/SM)
-  if (env) variant = atoi(env);
-  const int PB = (variant == 44 || variant == 42 || variant == 442) ? 4 : variant;
-  const bool multi = (dmax == 3) && pixel_step > 0 && (PB - 1) * pixel_step < cell;
+  const bool multi = (dmax == DMAX) && pixel_step > 0 && (SKEW_P - 1) * pixel_step < cell;
   if (multi) {
     if (fused) *fused = true;
-    switch (variant) {
-      case 2: return launch_multi<2, 5>(p, st);
-      case 3: return launch_multi<3, 4>(p, st);
-      case 44: return launch_multi<4, 4>(p, st);
-      case 42: return launch_multi<4, 3, true>(p, st);     // packed FFMA2 arithmetic
-      case 442: return launch_multi<4, 4, true>(p, st);
-      default: return launch_multi<4, 3>(p, st);
+    p.nseg = (p.npix + 32 * SKEW_P - 1) / (32 * SKEW_P);
+    p.list = nullptr;
+    if (staged && ctx) {
+      const int rc = launch_staged(ctx, g, p, st);
+      if (rc != SMK_ERR_UNSUPPORTED) return rc;
     }
+    const long long nblocks = ((long long)p.nqso * p.nseg + 3) / 4;
+    if (nblocks > 2147483647LL) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
+    skewers_multi_kernel<SKEW_P><<<(unsigned)nblocks, NT, 0, st>>>(p);
+    SMK_CUDA_OK(cudaGetLastError());
+    return SMK_OK;
   }
   int nchunk = (p.npix + NT - 1) / NT;
   long long nblocks = (long long)nchunk * p.nqso;
@@ -575,18 +797,34 @@ static int skewers_impl(smk_ctx* ctx, const smk_geom* g, const float* const fiel
   p.qso = qso_xyzr; p.npix_forest = npix_forest; p.rvec = rvec;
   p.delta_l = delta_l; p.eta_par = eta_par; p.vpar = vpar;
   p.delta_s = delta_s; p.fg_G = growthf; p.fg_a = fa; p.fg_b = fb; p.fg_c = fc; p.flux = flux;
-  { const char* e = getenv("SMK_SKEW_PF"); p.pf = e ? atoi(e) : 2; }
-  { const char* e = getenv("SMK_SKEW_PFD"); p.pfd = e ? atoi(e) : 1; if (p.pfd < 1 || p.pfd > 7) p.pfd = 1; }
   // largest step between consecutive pixels of the grid (uniform 0.2 Mpc/h in the reference); decides whether the
-  // register-blocked kernel may be used.  SMK_SKEWERS_SIMPLE=1 forces the one-pixel-per-thread kernel.
+  // register-blocked kernels may be used.  Parity-test switches: SMK_SKEWERS_SIMPLE=1 forces the one-pixel-per-thread
+  // kernel, SMK_SKEWERS_STAGED=0 the global-memory walk for every segment.
   double step = g->pixel_step;
   const char* env = getenv("SMK_SKEWERS_SIMPLE");
   if (env && env[0] == '1') step = 0.0;
+  env = getenv("SMK_SKEWERS_STAGED");
+  const bool staged = !(env && env[0] == '0');
   bool fused = false;
-  int rc = launch_skewers(p, g->dmax, step, smk_ctx_stream(ctx), &fused);
+  int rc = launch_skewers(ctx, g, p, g->dmax, step, staged, smk_ctx_stream(ctx), &fused);
   if (rc != SMK_OK || !flux || fused) return rc;
   // the one-pixel-per-thread kernel has no epilogue: FGPA as a separate pass over the rows
   return smk_fgpa(ctx, nqso, npix, delta_l, delta_s, eta_par, growthf, fa, fb, fc, flux);
+}
+
+extern "C" int smk_skewers_stats(smk_ctx* ctx, long long* segments, long long* handed_back, int box[3]) {
+  using namespace smk;
+  (void)ctx;
+  if (segments) *segments = g_last.nsegs;
+  if (handed_back) *handed_back = 0;
+  if (box) { box[0] = g_last.xw; box[1] = g_last.yw; box[2] = g_last.zl; }
+  if (g_last.handback && handed_back) {
+    int n = 0;
+    SMK_CUDA_OK(cudaMemcpyAsync(&n, g_last.handback, sizeof(int), cudaMemcpyDeviceToHost, g_last.st));
+    SMK_CUDA_OK(cudaStreamSynchronize(g_last.st));
+    *handed_back = n;
+  }
+  return SMK_OK;
 }
 
 extern "C" int smk_skewers(smk_ctx* ctx, const smk_geom* g, const float* const fields[10], int ix0, int nxs,

@@ -50,8 +50,14 @@ class SkewerGeometry(object):
         return ((1 + z) * self.cosmo.dist_hubble(z) / self.cosmo.dist_hubble(0.)
                 * cosmo_mod.lin_interp(self._dg[0], self._dg[1], z) / self.dgrowth0)
 
-    def c_geom(self):
-        return _lib.Geom(self.NX, self.NY, self.NZ, self.DX, self.DY, self.DZ, self.R0, self.dmax, self.pixel)
+    def c_geom(self, xyzr=None):
+        """smk_geom; xyzr (the catalogue's [n, 4] X, Y, Z, R_QSO) sizes the staged gather's box from the most oblique
+        sightline (include/smk.h: dir_x_max, dir_y_max)."""
+        dx = dy = 0.0
+        if xyzr is not None and len(xyzr):
+            dx = float(np.max(np.abs(xyzr[:, 0] / xyzr[:, 3])))
+            dy = float(np.max(np.abs(xyzr[:, 1] / xyzr[:, 3])))
+        return _lib.Geom(self.NX, self.NY, self.NZ, self.DX, self.DY, self.DZ, self.R0, self.dmax, self.pixel, dx, dy)
 
 
 def qso_lines_of_sight(geom, ra, dec, zqso, ra0, dec0):
@@ -103,7 +109,7 @@ class SkewerEngine(object):
             out = tuple(torch.full((nq, npix), float("nan"), dtype=torch.float32, device=self.device) for _ in range(3))
         q = torch.as_tensor(np.ascontiguousarray(xyzr, dtype=np.float64), device=self.device)
         nf = torch.as_tensor(np.ascontiguousarray(nforest, dtype=np.int32), device=self.device)
-        cg = g.c_geom()
+        cg = g.c_geom(np.asarray(xyzr, dtype=np.float64).reshape(-1, 4))
         _lib.check(self.lib.smk_skewers(self.ctx.handle(), C.byref(cg), fl, int(ix0), int(nxs), C.c_double(xmin), C.c_double(xmax),
                                         int(rsd), int(dla), nq, _ptr(q), _ptr(nf), _ptr(self.rvec), npix,
                                         _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))

@@ -30,7 +30,21 @@ def test_python_binding_matches_header():
     L = _lib.lib()
     for n in declared_functions():
         assert getattr(L, n) is not None
-    assert ctypes.sizeof(_lib.Geom) == 3 * 4 + 4 + 4 * 8 + 4 + 4 + 8     # smk_geom with C padding
+
+
+def test_geom_layout_matches_the_header(tmp_path):
+    """struct smk_geom: the ctypes mirror has the size and field offsets gcc gives the C declaration."""
+    import subprocess
+    from saclaymocks_b200._lib import Geom
+    src = tmp_path / "szg.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu",'
+                   'sizeof(smk_geom),offsetof(smk_geom,dx),offsetof(smk_geom,dmax),offsetof(smk_geom,pixel_step),'
+                   'offsetof(smk_geom,dir_y_max));return 0;}\n'
+                   % os.path.join(os.path.abspath(ROOT), "include", "smk.h"))
+    exe = str(tmp_path / "szg")
+    subprocess.check_call(["gcc", str(src), "-o", exe])
+    got = [int(v) for v in subprocess.check_output([exe]).split()]
+    assert got == [ctypes.sizeof(Geom), Geom.dx.offset, Geom.dmax.offset, Geom.pixel_step.offset, Geom.dir_y_max.offset]
 
 
 def test_qso_params_layout_matches_the_header(tmp_path):

@@ -238,6 +238,46 @@ def test_register_blocked_kernel_equals_simple_kernel(cuda, golden_ref32, monkey
         assert np.max(np.abs(a[m] - b[m])) < tol
 
 
+def test_staged_gather_equals_global_memory_gather(cuda, monkeypatch):
+    """The TMA-staged kernel (boxes of cells in shared memory) against the global-memory kernel on the same input:
+    the same walk over the same values, so the rows must be bit-identical; most segments must really be staged."""
+    from saclaymocks_b200 import _lib
+    from saclaymocks_b200 import spectra as sp
+    rng = np.random.default_rng(3)
+    NX, NY, NZ, dcell = 96, 64, 1536, 2.19
+    geom = sp.SkewerGeometry(NX, NY, NZ, dcell)
+    boxes = {k: torch.as_tensor(rng.standard_normal((NX, NY, NZ), dtype=np.float32), device=cuda) for k in sp.FIELDS}
+    nq = 300
+    hx = np.degrees(np.arctan(geom.LX / 2 / (geom.R0 + geom.LZ / 2))) * 1.05      # a few sightlines leave the box
+    hy = np.degrees(np.arctan(geom.LY / 2 / (geom.R0 + geom.LZ / 2))) * 1.05
+    ra = (190.0 + rng.uniform(-hx, hx, nq)).astype("f4")
+    dec = rng.uniform(-hy, hy, nq).astype("f4")
+    z = rng.uniform(1.9, 3.55, nq).astype("f4")
+    xyzr, nfor = sp.qso_lines_of_sight(geom, ra, dec, z, 190.0, 0.0)
+    eng = sp.SkewerEngine(geom, device=cuda)
+    for rsd, dla in ((True, True), (True, False), (False, False)):
+        staged = eng.read_spec(boxes, xyzr, nfor, rsd=rsd, dla=dla)
+        seg, back, box = _lib.skewers_stats()
+        assert seg > 0 and back < 0.25 * seg, (seg, back, box)                  # the staged kernel did the work
+        monkeypatch.setenv("SMK_SKEWERS_STAGED", "0")
+        plain = eng.read_spec(boxes, xyzr, nfor, rsd=rsd, dla=dla)
+        assert _lib.skewers_stats()[0] == 0
+        monkeypatch.delenv("SMK_SKEWERS_STAGED")
+        for a, b in zip(staged, plain):
+            assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+        assert int((~torch.isnan(staged[0])).sum()) > 100000
+    # two x-slabs with halo planes: the same rows again
+    out = None
+    for s_ in range(2):
+        lo, hi = max(s_ * NX // 2 - 3, 0), min((s_ + 1) * NX // 2 + 3, NX)
+        f = {k: boxes[k][lo:hi].contiguous() for k in sp.FIELDS}
+        out = eng.read_spec(f, xyzr, nfor, ix0=lo, xmin=geom.LX * s_ / 2 - geom.LX / 2,
+                            xmax=geom.LX * (s_ + 1) / 2 - geom.LX / 2, out=out)
+    full = eng.read_spec(boxes, xyzr, nfor)
+    for a, b in zip(out, full):
+        assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+
+
 def test_edge_cases_empty_and_out_of_range(cuda, golden_small):
     """Empty catalogue, quasars outside [zmin, zmax] (make_spectra.py:437-438), a sightline outside the slab."""
     from saclaymocks_b200 import spectra as sp
