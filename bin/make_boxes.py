@@ -2,6 +2,14 @@
 """GPU make_boxes: same CLI, file names and FITS headers as the reference's bin/make_boxes.py
 (argparse :137-150, products :242-431, FITS layout :110-117); the arithmetic runs in libsmk.so on a B200.
 
+Multi-GPU: launched with torchrun (one process per GPU, e.g. `torchrun --nproc-per-node 8 bin/make_boxes.py -NX 2560
+...`) the box is x-slab sharded over the ranks (saclaymocks_b200/chunk.py); every rank writes the files that hold its
+own planes -- the same file names and headers as one process would write (box-<ix>.fits and eta_*-<ix>.fits hold one
+plane each, boxln_<k>-<i>.fits and v?-<i>.fits NX/nHDU planes each, so nHDU must be a multiple of the rank count), with
+sigma reduced over all ranks.  boxk.npy (the resume file of the reference) is written as one y-slab shard per rank,
+boxk-<rank>of<n>.npy.  `-PkDir gpu` evaluates the spectral weight tables on the GPU from the P(k) splines
+(smk_pk_weights, bit-equal to the P-file to > 99.9 %) instead of reading the 4 x NX*NY*(NZ/2+1) table file.
+
 Extra option: -noise {philox,mt19937}.  `mt19937` draws the white noise on the host exactly like the reference
 (np.random.seed(seed) + one np.random.normal plane per iz, make_boxes.py:46-48, 163-171) so that a given seed
 reproduces the reference's boxes; `philox` (default) draws it inside the forward z pass on the GPU.
@@ -34,6 +42,78 @@ def write_box(box, boxfilename, nHDU, Dcell, NX, NY, NZ, sigma, seed):
 
 def nfiles(prefix):
     return len(glob.glob(prefix + "*"))
+
+
+def main_sharded(args, seed, rsd, NX, NY, NZ, dd):
+    """One rank of a torchrun launch: this rank's x-slab of every product, written to the files that hold its planes."""
+    import torch
+    import torch.distributed as dist
+    from saclaymocks_b200.chunk import ChunkPipeline
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    sd = torch.tensor([seed], dtype=torch.int64, device=dev)       # a seed drawn at random must be the same on every rank
+    dist.broadcast(sd, 0)
+    seed = int(sd.item())
+    Dcell, nHDU, outDir = args.pixel, args.nHDU, args.outDir
+    if NX % world or NY % world or nHDU % world:
+        raise ValueError("NX, NY and nHDU must be multiples of the number of ranks ({})".format(world))
+    t_init = time.time()
+    pipe = ChunkPipeline(NX, NY, NZ, Dcell, device=dev, rank=rank, nranks=world, rsd=rsd)
+    bs = pipe.bs
+    bs.dgrowth0 = float(dd[0])
+    nxl, nyl = NX // world, NY // world
+    if args.PkDir == "gpu":
+        W = {k: bs.weight_table(k) for k in ("Pln1", "Pln2", "Pln3", "P0")}
+    else:
+        Pfilename = args.PkDir + ("/P{}.fits".format(NX) if (NY == NX and NZ == NX) else
+                                  "/P{}-{}-{}.fits".format(NX, NY, NZ))
+        W = {k: np.ascontiguousarray(fitsio.read(Pfilename, ext=k)[:, rank * nyl:(rank + 1) * nyl])
+             for k in ("Pln1", "Pln2", "Pln3", "P0")}
+    pipe.set_weights(W)
+    noise = None
+    if args.noise == "mt19937":            # the reference's stream: every rank draws all of it and keeps its own planes
+        np.random.seed(seed)
+        slab_noise = np.zeros((nxl, NY, NZ), dtype=np.float32)
+        for iz in range(NZ):
+            slab_noise[:, :, iz] = np.float32(np.random.normal(size=[NX, NY]))[rank * nxl:(rank + 1) * nxl]
+        noise = torch.as_tensor(slab_noise, device=dev)
+    products = [n for n in bs_products() if rsd or n.startswith("box")]
+    pipe.step_boxes(seed=seed, noise=noise, products=products)
+    torch.cuda.synchronize()
+    np.save(outDir + "/boxk-{}of{}.npy".format(rank, world), bs.boxk_to_numpy(pipe.boxk))
+    if rank == 0:
+        np.save(outDir + "/seed_boxk.npy", seed)
+    sig = pipe.sigmas()                                                        # all-reduced over the ranks
+    for name in products:
+        if not (sig[name] > 0) or np.isnan(sig[name]):                         # make_boxes.py:100-105
+            raise ValueError("box {} is null".format(name))
+        box = pipe.interior(name).cpu().numpy()
+        per_plane = name == "box" or name.startswith("eta_")
+        nfile = NX if per_plane else nHDU
+        per = NX // nfile                                                      # planes per file
+        for i in range(rank * nxl // per, (rank + 1) * nxl // per):
+            f = fitsio.FITS(outDir + "/" + name + "-{}.fits".format(i), "rw", clobber=True)
+            f.write(box[i * per - rank * nxl:(i + 1) * per - rank * nxl],
+                    header={"DX": Dcell, "DY": Dcell, "DZ": Dcell, "NX": NX, "NY": NY, "NZ": NZ})
+            if i == 0:
+                f[0].write_key("sigma", np.float32(sig[name]), comment="std of the box")
+                f[0].write_key("seed", np.int32(seed), comment="seed used to generate randoms")
+            f.close()
+        if rank == 0:
+            print(name, "sigma = {}".format(sig[name]))
+    dist.barrier()
+    if rank == 0:
+        print("NX=", NX, "ranks=", world)
+        print("Took {}s".format(time.time() - t_init))
+    dist.destroy_process_group()
+
+
+def bs_products():
+    from saclaymocks_b200.boxes import PRODUCTS
+    return PRODUCTS
 
 
 def main():
@@ -73,6 +153,8 @@ def main():
     if rsd and constant.omega_M_0 != om:                                       # make_boxes.py:309-311
         raise ValueError("Omega_M_0 in constant ({}) != OM in dgrowth file ({})".format(constant.omega_M_0, om))
 
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:                            # torchrun: x-slab sharded over the ranks
+        return main_sharded(args, seed, rsd, NX, NY, NZ, dd)
     dev = torch.device("cuda:0")
     bs = BoxSynth(NX, NY, NZ, Dcell, device=dev)
     bs.dgrowth0 = float(dd[0])

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """GPU make_spectra: same CLI and output files as the reference's bin/make_spectra.py (argparse :146-161, slab
 loader :196-295, QSO-file selection :324-382, spectra files :528-597).  The per-quasar Python loop (:412-522) is one
-batched smk_skewers launch over all quasars of the slab."""
+batched smk_skewers launch over all quasars of the slab.
+
+Multi-GPU: the reference runs one process per slice (-i); launched with torchrun and WITHOUT -i, rank r works through the
+slices r, r + ranks, ... on its own GPU (cuda:LOCAL_RANK) and writes the same spectra-<slice>-<hdu>.fits.gz files."""
 import argparse
 import os
 import sys
@@ -33,10 +36,17 @@ def main():
     parser.add_argument("-dla", default="False")
     parser.add_argument("-dgrowthfile", default=None)
     args = parser.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    slices = [args.i] if args.i is not None else list(range(rank, args.N, world))
+    for iSlice in slices:
+        run_slice(args, iSlice, t_init)
+
+
+def run_slice(args, iSlice, t_init):
     import torch
     from saclaymocks_b200 import spectra as sp
 
-    iSlice, NSlice, dmax = args.i, args.N, args.dmax
+    NSlice, dmax = args.N, args.dmax
     rsd, dla = str2bool(args.rsd), str2bool(args.dla)
     boxdir = args.boxdir
     print("Begining of MakeSpectra - {}".format(iSlice))
@@ -54,7 +64,7 @@ def main():
     geom = sp.SkewerGeometry(nHDU, NY, NZ, DX, zmin=args.zmin, zmax=args.zmax, pixel=args.pixel, dmax=dmax)
     iXmin = max((iSlice * nHDU) // NSlice - dmax, 0)                     # make_spectra.py:220-221
     iXmax = min(((iSlice + 1) * nHDU) // NSlice + dmax, nHDU)
-    dev = torch.device("cuda:0")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     t0 = time.time()
 
     def load_planes(name):
@@ -100,7 +110,7 @@ def main():
             ra0, dec0 = h["RA0"], h["DEC0"]
     if not qsos or sum(len(q) for q in qsos) == 0:
         print("No QSO read. ==> Exit.")
-        sys.exit(0)
+        return
     qsos = np.concatenate(qsos)
     print(len(qsos), "QSO read")
     if args.NQSO > 0:

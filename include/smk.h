@@ -200,6 +200,17 @@ int smk_smallscale(smk_ctx* ctx, int nqso, int nfft, int npix, const float* nois
 int smk_fgpa(smk_ctx* ctx, int nqso, int npix, const float* delta_l, const float* delta_s, const float* eta_par,
              const float* growthf, const float* a, const float* b, const float* c, float* flux);
 
+/* ---- 1-D power spectrum estimator on the GPU (py/SaclayMocks/powerspectrum.py:204-238):
+ * P1D_1spectrum(delta, DX) = |rfft(delta)|^2 DX / n of the window of nfft pixels that starts at first[q] in row q of
+ * rows [nqso][npix], accumulated over the rows like ComputeP1D (every spectrum has the same k grid here, so the profile
+ * histogram of the reference is a per-wavenumber mean).  Rows with fewer than nfft valid pixels (nvalid[q], counted from
+ * first[q]) are skipped.  mean != NULL: the window is first turned into the contrast rows / mean[q] - 1 (transmission
+ * F -> delta_F).  first / nvalid NULL: window at 0 / all npix pixels valid.
+ * sums: device double [2][nfft/2+1], ACCUMULATED: sum of P(k_j) and sum of P(k_j)^2, k_j = 2 pi j / (nfft pixel);
+ * nused: device counter of the rows that contributed.  nfft: power of two in [256, 8192]. */
+int smk_p1d(smk_ctx* ctx, int nqso, int npix, int nfft, const float* rows, const int* first, const int* nvalid,
+            const float* mean, double pixel, double* sums, unsigned long long* nused);
+
 /* ---- skewers with the FGPA fused into the gather's epilogue (make_spectra.py:90-139 followed by util.py:421-433 for
  * the pixels this slab owns): smk_skewers, then flux = exp(-a exp(b G (delta_l + delta_s + c eta_par))) from the values
  * still in registers -- the rows delta_l / eta_par are written once and not read back.  delta_s [nqso][npix] comes from

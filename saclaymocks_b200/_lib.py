@@ -15,7 +15,7 @@ EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy",
            "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
            "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
            "smk_make_boxes_host", "smk_skewers", "smk_skewers_fgpa", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
-           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light", "smk_exchange_set_sms", "smk_skewers_stats")
+           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light", "smk_exchange_set_sms", "smk_skewers_stats", "smk_p1d")
 
 
 class SmkError(RuntimeError):
@@ -67,6 +67,7 @@ def lib():
     L.smk_skewers_fgpa.argtypes = L.smk_skewers.argtypes + [vp, vp, vp, vp, vp, vp]
     L.smk_skewers_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(i)]
     L.smk_smallscale.argtypes = [vp, i, i, i, vp, u64, vp, vp, vp, vp, vp, vp]
+    L.smk_p1d.argtypes = [vp, i, i, i, vp, vp, vp, vp, d, vp, vp]
     L.smk_fgpa.argtypes = [vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.smk_pk_weights.argtypes = [vp, vp, vp, i, vp]
     L.smk_exchange_create.argtypes = [vp, i]

@@ -105,7 +105,8 @@ class ChunkPipeline(object):
         sel = np.where(keep & touch)[0]
         ids = np.arange(len(nfor), dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
         self.cat = dict(sel=sel, xyzr=np.ascontiguousarray(xyzr[sel]), nfor=np.ascontiguousarray(nfor[sel]),
-                        ids=ids[sel], z=np.asarray(z)[sel], xmin=xmin, xmax=xmax, n_total=len(nfor))
+                        ids=ids[sel], z=np.asarray(z)[sel], xmin=xmin, xmax=xmax, n_total=len(nfor),
+                        kept=np.where(keep)[0], xyzr_kept=np.ascontiguousarray(xyzr[keep]))
         nq, npix = len(sel), g.npixeltot
         self.cat["xyzr_d"] = torch.as_tensor(self.cat["xyzr"], device=self.device)
         self.cat["nfor_d"] = torch.as_tensor(self.cat["nfor"], device=self.device)
@@ -304,6 +305,26 @@ class ChunkPipeline(object):
     def step(self, seed=0):
         self.step_boxes(seed)
         self.step_skewers(seed)
+
+    def gather_rows(self):
+        """Complete spectra rows on the home rank of every quasar (the slab that contains the quasar itself: the
+        reference's HDU / slice id, draw_qso.py:495).  The reference stitches a sightline's pieces through the file
+        system (make_spectra.py writes one piece per slice, merge_spectra.py:385-406 concatenates and sorts them); here
+        each of delta_l, eta_par, vpar, flux, delta_s makes one all-to-all and the pieces are merged by position.
+        Returns {"index": catalogue indices of this rank's quasars, "delta_l", "eta_par", "vpar", "flux", "delta_s":
+        device tensors [n_home, npix]}; pixels outside the box keep NaN (they are in no slice of the reference either)."""
+        c, g = self.cat, self.geom
+        names = ("delta_l", "eta_par", "vpar", "flux")
+        if self.nranks == 1:
+            res = {"index": c["sel"]}
+            res.update({k: t for k, t in zip(names, self.out)})
+            res["delta_s"] = self.delta_s
+            return res
+        plan = slab.row_gather_plan(c["xyzr_kept"], g.R_vec[0], g.R_vec[-1], self.nranks, g.LX, self.rank)
+        res = {"index": c["kept"][plan["home_qso"]]}
+        for k, t in zip(names + ("delta_s",), self.out + (self.delta_s,)):
+            res[k] = slab.exchange_rows(t, plan, group=self.group)
+        return res
 
     # ------------------------------------------------------------------ quasars (draw_qso.py on the resident boxes)
     def set_footprint(self, ra0, dec0, dra, ddec, zmin=1.8, zmax=3.6, chunk=1):

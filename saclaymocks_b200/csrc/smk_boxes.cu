@@ -298,7 +298,10 @@ int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, floa
 template <int M>
 struct ZTraits {
   using P = typename PlanFor<M>::type;
-  static constexpr int LINES = (M > 1024) ? 4 : 16;
+#ifndef SMK_Z_LINES
+#define SMK_Z_LINES 16   // lines per tile of the z passes (M <= 1024); 8 halves the tile (4 CTAs of 128 threads per SM)
+#endif
+  static constexpr int LINES = (M > 1024) ? 4 : ((M >= 512) ? SMK_Z_LINES : 16);
   static constexpr int NT_ = (M % 3 == 0) ? LINES * M / 48 / 32 * 32 : LINES * M / 32;
   static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
   // PERM: two-stage plan R0.R1 with a radix-32 first stage, run without the re-sorting last stage (which would need
@@ -308,7 +311,14 @@ struct ZTraits {
   static constexpr bool PERM = (P::S == 2 && P::radix(0) >= 32);
   static constexpr int R0 = P::radix(0), R1 = PERM ? P::radix(1) : 1;
   static constexpr int LP_ = PERM ? M + M / R1 : M;
-  static constexpr int LP = LP_ + 1 - LP_ % 2;   // odd pitch: column accesses (lane = line) are conflict free
+  // pitch: the lanes of a half-warp are LINES lines x 16 / LINES consecutive positions of one stage; with a pitch of
+  // 16 / LINES (mod 16) float2 they fall on 16 different bank pairs (LINES == 16: any odd pitch)
+  static constexpr int pitch(int least) {
+    int lp = least;
+    while (lp % 16 != (16 / LINES) % 16) ++lp;
+    return lp;
+  }
+  static constexpr int LP = (LINES == 16) ? LP_ + 1 - LP_ % 2 : pitch(LP_);
   __device__ static __forceinline__ int idx(int p) { return PERM ? p + p / R1 : p; }         // padded position
   __device__ static __forceinline__ int nat(int k) { return PERM ? idx((k % R0) * R1 + k / R0) : k; }   // where output k sits
 };
@@ -330,6 +340,35 @@ __device__ __forceinline__ void z_tile_fft(float2* sm, const float2* __restrict_
   } else {
     dif_stages_smem<P, 0, P::S - 1, INV, LINES, LP, 1, NT>(sm, tw, 2);
     dif_last_resort_smem<P, INV, LINES, LP, 1, NT>(sm, tw, 2);
+  }
+}
+
+// Inverse z pass with the last DIF stage fused into the store (plans of >= 2 stages): the last stage has no twiddles and
+// its butterfly b = pos(n0) / RL produces the natural outputs n0 + q M/RL, so a warp whose lanes take CONSECUTIVE n0
+// runs it straight from shared memory into coalesced global stores -- the re-sort (one shared-memory write + read of
+// the tile) and the separate store loop's read disappear (8 -> 6 passes over the tile in shared memory; the kernel is
+// bound by that pipe).  Consecutive n0 read positions M/R0 apart: one float2 of padding after every M/R0 positions
+// makes that stride odd in units of 8 bytes, i.e. conflict free for the 16 lanes of a half-warp.
+template <int M>
+struct C2RTraits {
+  using ZT = ZTraits<M>;
+  using P = typename ZT::P;
+  static constexpr int R0 = P::radix(0), RL = P::radix(P::S - 1), BLK = M / R0, NB = M / RL;
+  static constexpr bool FUSE = (P::S >= 2) && !ZT::PERM && (BLK % 2 == 0) && (BLK % RL == 0) && (M >= 32);
+  static constexpr int LP_ = M + R0;
+  static constexpr int LP = FUSE ? (ZT::LINES == 16 ? (LP_ + 1 - LP_ % 2) : ZT::pitch(LP_)) : ZT::LP;
+  __device__ static __forceinline__ int idx(int p) { return FUSE ? p + p / BLK : ZT::idx(p); }
+};
+
+// stages [S0, S1) in place through the padded index, a barrier after each
+template <class CT, int S0, int S1, int LINES, int NT, int LP>
+__device__ __forceinline__ void c2r_stages(float2* sm, const float2* __restrict__ tw) {
+  if constexpr (S0 < S1) {
+    auto ld = [&](int line, int ppos, int, int) { return sm[line * LP + ppos]; };          // padded positions
+    auto st = [&](int line, int ppos, float2 val) { sm[line * LP + ppos] = val; };
+    dif_stage<typename CT::P, S0, true, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, CT::BLK>(ld, st, tw, 2);
+    __syncthreads();
+    c2r_stages<CT, S0 + 1, S1, LINES, NT, LP>(sm, tw);
   }
 }
 
@@ -409,9 +448,11 @@ struct C2RParams {
 };
 
 template <int M>
-__global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
+// two CTAs of (M >= 512: 98 KB) share an SM: the register allocation has to leave room for both
+__global__ void __launch_bounds__(ZTraits<M>::NT, (M >= 512) ? 32 / ZTraits<M>::LINES : 1) c2r_z_kernel(C2RParams p) {
   using ZT = ZTraits<M>;
-  constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = ZTraits<M>::LP;
+  using CT = C2RTraits<M>;
+  constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = CT::LP;
   extern __shared__ float2 sm[];
   __shared__ double red[2][NT / 32];
   const long long line0 = (long long)blockIdx.x * LINES;
@@ -444,8 +485,8 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
         const float2 wc = make_float2(w[i].x, -w[i].y);   // exp(+2 pi i k / NZ)
         const float2 A = make_float2(av.x + bv.x, av.y - bv.y);
         const float2 B = cmul(make_float2(av.x - bv.x, av.y + bv.y), wc);
-        row[ZT::idx(k)] = make_float2(A.x - B.y, A.y + B.x);        // A + iB
-        if (k != 0 && k != M - k) row[ZT::idx(M - k)] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
+        row[CT::idx(k)] = make_float2(A.x - B.y, A.y + B.x);        // A + iB
+        if (k != 0 && k != M - k) row[CT::idx(M - k)] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
       }
     }
   }
@@ -458,22 +499,52 @@ __global__ void __launch_bounds__(ZTraits<M>::NT) c2r_z_kernel(C2RParams p) {
     const int n128 = (int)(nl * p.pitch * 8 / 128);
     for (int i = threadIdx.x; i < n128; i += NT) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + 128LL * i) : "memory");
   }
-  z_tile_fft<M, true>(sm, p.tw);
   // ---- store x[2n], x[2n+1] = z[n] / N, accumulate sum and sum of squares
   float s1 = 0.f, s2 = 0.f;
   const float rnorm = __frcp_rn(p.norm);
   float2* out2 = reinterpret_cast<float2*>(p.out);
-  for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
-    if (line0 + line < p.nlines) {
-      float2* dst = out2 + (line0 + line) * M;
+  if constexpr (CT::FUSE) {
+    using P = typename CT::P;
+    constexpr int RL = CT::RL, NB = CT::NB;
+    c2r_stages<CT, 0, P::S - 1, LINES, NT, LP>(sm, p.tw);
+    // last stage: lane = natural output index n0 (butterfly pos(n0) / RL), outputs n0 + q NB go straight to HBM
+    for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
+      if (line0 + line < p.nlines) {
+        float2* dst = out2 + (line0 + line) * M;
+        const float2* row = sm + line * LP;
+#pragma unroll 2
+        for (int n0 = threadIdx.x & 31; n0 < NB; n0 += 32) {
+          const int pb = P::pos(n0);
+          float2 v[RL];
+#pragma unroll
+          for (int t = 0; t < RL; ++t) v[t] = row[CT::idx(pb + t)];
+          Butterfly<RL, true>::run(v);
+#pragma unroll
+          for (int q = 0; q < RL; ++q) {
+            float2 z = v[q];
+            z.x = fdiv_fast(z.x, p.norm, rnorm);
+            z.y = fdiv_fast(z.y, p.norm, rnorm);
+            __stcs(dst + n0 + q * NB, z);            // written once, read much later: streaming store
+            s1 += z.x + z.y;
+            s2 += z.x * z.x + z.y * z.y;
+          }
+        }
+      }
+    }
+  } else {
+    z_tile_fft<M, true>(sm, p.tw);
+    for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
+      if (line0 + line < p.nlines) {
+        float2* dst = out2 + (line0 + line) * M;
 #pragma unroll 8
-      for (int n = threadIdx.x & 31; n < M; n += 32) {
-        float2 z = sm[line * LP + ZT::nat(n)];
-        z.x = fdiv_fast(z.x, p.norm, rnorm);
-        z.y = fdiv_fast(z.y, p.norm, rnorm);
-        __stcs(dst + n, z);            // written once, read much later: streaming store
-        s1 += z.x + z.y;
-        s2 += z.x * z.x + z.y * z.y;
+        for (int n = threadIdx.x & 31; n < M; n += 32) {
+          float2 z = sm[line * LP + ZT::nat(n)];
+          z.x = fdiv_fast(z.x, p.norm, rnorm);
+          z.y = fdiv_fast(z.y, p.norm, rnorm);
+          __stcs(dst + n, z);            // written once, read much later: streaming store
+          s1 += z.x + z.y;
+          s2 += z.x * z.x + z.y * z.y;
+        }
       }
     }
   }
@@ -538,7 +609,7 @@ int launch_r2c_z(int NZ, const float* in, float2* out, long long nlines, int pit
 
 template <int M>
 static int launch_c2r_t(const C2RParams& p, cudaStream_t st) {
-  size_t smem = (size_t)ZTraits<M>::LINES * ZTraits<M>::LP * sizeof(float2);
+  size_t smem = (size_t)ZTraits<M>::LINES * C2RTraits<M>::LP * sizeof(float2);
   unsigned grid = (unsigned)((p.nlines + ZTraits<M>::LINES - 1) / ZTraits<M>::LINES);
   auto kern = c2r_z_kernel<M>;
   if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

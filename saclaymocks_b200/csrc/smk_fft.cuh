@@ -378,8 +378,11 @@ struct NoPre {
 // ld(line, pos, i, t): i = task slot of this thread within the current batch, t = input index of the butterfly (both compile-time after
 // unrolling, so a caller can keep per-element side data in a register array indexed [i][t]);
 // pre(line, pos, i, t, v) runs after ALL loads of the thread have been issued (fused multiply of the first stage).
+// PADBLK > 0 (in-place stages only): the tile is stored with one element of padding after every PADBLK = N / R0
+// positions (position p at p + p / PADBLK); the stage hands ld / st the PADDED position, computed from the block index
+// once per butterfly instead of a division per element.
 template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store, class Pre = NoPre,
-          int BATCH = 0>
+          int BATCH = 0, int PADBLK = 0>
 __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __restrict__ tw, int twmul,
                                           Pre pre = Pre()) {
   constexpr int R = P::radix(STAGE);
@@ -395,6 +398,11 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
   // for registers, which lets the fused-multiply passes keep 3 CTAs per SM)
   constexpr int TB = (BATCH > 0 && BATCH < TPT) ? BATCH : TPT;
   static_assert(OUT != OUT_RESORT || TB == TPT, "a re-sorting stage reads everything before it writes");
+  static_assert(PADBLK == 0 || (OUT == OUT_INPLACE && (STAGE == 0 ? MQ == PADBLK : PADBLK % M == 0)),
+                "padded layout: in-place stages of a plan whose first stage has stride PADBLK");
+  // padded position of element t of the butterfly at (b, o): stage 0 spans the pads (one per t), later stages sit
+  // inside one PADBLK block (b * M / PADBLK pads before it)
+  constexpr int TPAD = (PADBLK > 0 && STAGE == 0) ? 1 : 0;
   constexpr bool EVEN = (NTASK % NT == 0);
   constexpr int JSTEP = NT / LINES;
   // a thread always works on the same line: task = threadIdx.x + i*NT  =>  line = threadIdx.x % LINES
@@ -409,8 +417,9 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
       const int j = j0 + (i0 + ii) * JSTEP;
       if (i0 + ii < TPT && (EVEN || j < NB)) {
         const int b = j / MQ, o = j - b * MQ;
+        const int base = b * M + o + ((PADBLK > 0 && STAGE > 0) ? b / (PADBLK > 0 ? PADBLK / M : 1) : 0);
 #pragma unroll
-        for (int t = 0; t < R; ++t) v[ii][t] = ld(line, b * M + o + t * MQ, ii, t);
+        for (int t = 0; t < R; ++t) v[ii][t] = ld(line, base + t * (MQ + TPAD), ii, t);
       }
     }
     if (OUT == OUT_RESORT) __syncthreads();
@@ -436,8 +445,9 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
 #pragma unroll
           for (int q = 0; q < R; ++q) st(line, nb + q * (P::N / R), v[ii][q]);
         } else {
+          const int base = b * M + o + ((PADBLK > 0 && STAGE > 0) ? b / (PADBLK > 0 ? PADBLK / M : 1) : 0);
 #pragma unroll
-          for (int q = 0; q < R; ++q) st(line, b * M + o + q * MQ, v[ii][q]);
+          for (int q = 0; q < R; ++q) st(line, base + q * (MQ + TPAD), v[ii][q]);
         }
       }
     }

@@ -22,6 +22,10 @@
 
 #include "smk_internal.h"
 
+#ifndef SMK_SKEW_VARIANT_DEFAULT
+#define SMK_SKEW_VARIANT_DEFAULT 41   // 4 pixels per thread, 1 field per stage, 12 warps per SM
+#endif
+
 namespace smk {
 
 struct SkewerParams {
@@ -66,6 +70,14 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
       : "=f"(d.x), "=f"(d.y)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
+}
+
+// exp(x) for the Gaussian window weights: ex2.approx(x log2 e), what __expf evaluates for arguments that cannot
+// underflow (here x >= -6.2), without its range check and the branches that come with it
+__device__ __forceinline__ float exp_weight(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
 }
 
 // FGPA of one pixel, the float32 arithmetic of fgpa_kernel (smk_spectra1d.cu) operation for operation
@@ -192,16 +204,20 @@ __device__ __forceinline__ void pixel_xyz(const SkewerParams& p, int q, int i, d
 }
 
 // Per-thread state of P consecutive pixels: cells, in-cell offsets, the union window and the separable weights along
-// y and z (x weights are re-evaluated inside the walk, one exponential per pixel and window plane).
+// y and z (x weights are re-evaluated inside the walk, one exponential per pixel and window plane).  Pixels are packed
+// in pairs (2h, 2h+1) wherever a weight multiplies both with one FMUL2.
 template <int P>
 struct PixelGroup {
+  static_assert(P % 2 == 0 && P <= 4, "pixels are processed in pairs; xlo packs one byte per pixel");
   unsigned actmask;            // pixels of this thread that are owned by the slab and inside the forest
   int bx, by, bz;              // lowest cell of the union of the windows' centres
   int nxu, nyu;                // union window extent along x / y (7 or 8)
   int tz;                      // highest centre cell along z
   int dix[P];                  // centre cell of pixel k minus bx (100 for an inactive pixel: zero weight everywhere)
-  float ox[P];                 // cell centre - pixel along x
-  float wy[P][WU];             // y weights over the union window
+  float ox[P];                 // cell centre - pixel along x (set-up only; the walk uses tx0 / xlo)
+  float tx0[P];                // x offset of window plane a = 0 from pixel k: plane a sits at tx0 + a * dx
+  unsigned xlo;                // first window plane of pixel k in bits [8k, 8k+8) (its window is planes xlo .. xlo + 6)
+  float2 wy2[P / 2][WU];       // y weights over the union window of the pixel pair (2h, 2h+1)
   float2 wz2[P][WU / 2];       // z weights over the union window, packed in pairs of cells
   float syz[P];                // (sum of y weights) * (sum of z weights)
 };
@@ -254,6 +270,9 @@ __device__ __forceinline__ bool pixel_group_setup(const SkewerParams& p, int q, 
   for (int k = 0; k < P; ++k) {
     const bool act = (g.actmask >> k) & 1;
     g.dix[k] = act ? ix[k] - bx : 100;      // an inactive pixel gets zero weight everywhere
+    g.tx0[k] = (float)(-DMAX - g.dix[k]) * (float)p.dx + g.ox[k];
+    if (k == 0) g.xlo = 0;
+    g.xlo |= (unsigned)g.dix[k] << (8 * k);
     const int diy = iy[k] - by, diz = iz[k] - bz;
     float sy = 0.f, sz = 0.f;
     float wz[WU];
@@ -261,16 +280,37 @@ __device__ __forceinline__ bool pixel_group_setup(const SkewerParams& p, int q, 
     for (int c = 0; c < WU; ++c) {
       const int mz = c - DMAX - diz, my = c - DMAX - diy;
       const float tzz = mz * fdz + oz[k], tyy = my * fdy + oy[k];
-      wz[c] = (act && mz >= -DMAX && mz <= DMAX) ? __expf(-tzz * tzz * inv_sig2) : 0.f;
-      g.wy[k][c] = (act && my >= -DMAX && my <= DMAX) ? __expf(-tyy * tyy * inv_sig2) : 0.f;
+      wz[c] = (act && mz >= -DMAX && mz <= DMAX) ? exp_weight(-tzz * tzz * inv_sig2) : 0.f;
+      const float wyc = (act && my >= -DMAX && my <= DMAX) ? exp_weight(-tyy * tyy * inv_sig2) : 0.f;
+      if (k & 1) g.wy2[k / 2][c].y = wyc; else g.wy2[k / 2][c].x = wyc;
       sz += wz[c];
-      sy += g.wy[k][c];
+      sy += wyc;
     }
 #pragma unroll
     for (int j = 0; j < WU / 2; ++j) g.wz2[k][j] = make_float2(wz[2 * j], wz[2 * j + 1]);
     g.syz[k] = sy * sz;
   }
   return true;
+}
+
+// a lane without pixels in a warp that still has some: zero weights everywhere
+template <int P>
+__device__ __forceinline__ void pixel_group_idle(PixelGroup<P>& g) {
+  g.actmask = 0;
+  g.bx = g.by = g.bz = g.tz = 0;
+  g.nxu = g.nyu = 2 * DMAX + 1;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    g.dix[k] = 100; g.ox[k] = 0.f; g.syz[k] = 1.f; g.tx0[k] = 0.f;
+    if (k == 0) g.xlo = 0;
+    g.xlo |= 100u << (8 * k);
+#pragma unroll
+    for (int j = 0; j < WU / 2; ++j) g.wz2[k][j] = make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int h = 0; h < P / 2; ++h)
+#pragma unroll
+    for (int c = 0; c < WU; ++c) g.wy2[h][c] = make_float2(0.f, 0.f);
 }
 
 // whole union window inside the slab (no index clamping needed)
@@ -280,27 +320,57 @@ __device__ __forceinline__ bool group_interior(const SkewerParams& p, const Pixe
          g.by - DMAX + g.nyu <= p.ny && g.bz - DMAX >= 0 && g.tz + DMAX < p.nz;
 }
 
-// Running results of a pixel group: fields arrive in the order delta, eta_xx, eta_yy, eta_zz, eta_xy, eta_xz, eta_yz,
-// vx, vy, vz and are contracted on the fly (make_spectra.py:116-127), float64 like the reference's x*eta*x products.
-template <int P>
-struct PixelResult {
-  float d0[P];
-  double eta[P], vel[P];
+// Contraction of the gathered fields along the line of sight (make_spectra.py:116-127).  Every pixel of a sightline
+// has the same direction u = (X, Y, Z) / R_QSO, and the reference's x_i eta_ij x_j / r^2 and v_i x_i / r are
+// homogeneous of degree zero in the pixel position, so they are evaluated with u once per sightline:
+// eta_par = u_i eta_ij u_j / |u|^2, v_par = v_i u_i / |u| (float64 like the reference's products).
+// The six / three coefficients are evaluated in float64 from the catalogue's float64 (X, Y, Z, R) and rounded to
+// float32 once; the sums of six (three) float32 terms then carry ~1e-7 of the largest eta_ij (v_i), against the
+// 5e-6 the rows are compared at.
+struct Direction {
+  float ux, uy, uz, inv_u2, inv_u;
 };
+__device__ __forceinline__ Direction sightline_direction(const SkewerParams& p, int q) {
+  const double R = p.qso[4 * q + 3];
+  const double ux = p.qso[4 * q] / R, uy = p.qso[4 * q + 1] / R, uz = p.qso[4 * q + 2] / R;
+  const double u2 = ux * ux + uy * uy + uz * uz;
+  Direction d;
+  d.ux = (float)ux; d.uy = (float)uy; d.uz = (float)uz;
+  d.inv_u2 = (float)(1.0 / u2);
+  d.inv_u = (float)(1.0 / sqrt(u2));
+  return d;
+}
+// coefficient of field f (delta, eta_xx, eta_yy, eta_zz, eta_xy, eta_xz, eta_yz, vx, vy, vz) in eta_par / v_par
+__device__ __forceinline__ float field_coefficient(const Direction& d, int f) {
+  switch (f) {
+    case 1: return d.ux * d.ux * d.inv_u2;
+    case 2: return d.uy * d.uy * d.inv_u2;
+    case 3: return d.uz * d.uz * d.inv_u2;
+    case 4: return 2.f * d.ux * d.uy * d.inv_u2;
+    case 5: return 2.f * d.ux * d.uz * d.inv_u2;
+    case 6: return 2.f * d.uy * d.uz * d.inv_u2;
+    case 7: return d.ux * d.inv_u;
+    case 8: return d.uy * d.inv_u;
+    case 9: return d.uz * d.inv_u;
+    default: return 1.f;
+  }
+}
 
 template <int P>
-__device__ __forceinline__ void result_add(PixelResult<P>& r, int f, int k, float val, double xv, double yv, double zv) {
-  switch (f) {
-    case 0: r.d0[k] = val; break;
-    case 1: r.eta[k] += xv * (double)val * xv; break;
-    case 2: r.eta[k] += yv * (double)val * yv; break;
-    case 3: r.eta[k] += zv * (double)val * zv; break;
-    case 4: r.eta[k] += 2 * xv * (double)val * yv; break;
-    case 5: r.eta[k] += 2 * xv * (double)val * zv; break;
-    case 6: r.eta[k] += 2 * yv * (double)val * zv; break;
-    case 7: r.vel[k] += (double)val * xv; break;
-    case 8: r.vel[k] += (double)val * yv; break;
-    default: r.vel[k] += (double)val * zv; break;
+struct PixelResult {
+  float d0[P], eta[P], vel[P];
+};
+
+// fold field f of one walk (two partial sums per pixel) into the running results
+template <int P>
+__device__ __forceinline__ void fold_field(int f, float coef, const float2 (&acc2)[P], const float (&inv_sw)[P],
+                                           PixelResult<P>& r) {
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const float val = (acc2[k].x + acc2[k].y) * inv_sw[k];
+    if (f == 0) r.d0[k] = val;
+    else if (f <= 6) r.eta[k] = fmaf(coef, val, r.eta[k]);
+    else r.vel[k] = fmaf(coef, val, r.vel[k]);
   }
 }
 
@@ -311,194 +381,131 @@ __device__ __forceinline__ void result_store(const SkewerParams& p, int q, int i
   for (int k = 0; k < P; ++k) {
     if (!((actmask >> k) & 1)) continue;
     const size_t o = (size_t)q * p.npix + i0 + k;
-    double xv, yv, zv;
-    pixel_xyz<P>(p, q, i0 + k, xv, yv, zv);
-    const double RR = xv * xv + yv * yv + zv * zv;
     const float dl = r.d0[k];
-    const float ep = nf >= 7 ? (float)(r.eta[k] / RR) : 0.f;
+    const float ep = nf >= 7 ? r.eta[k] : 0.f;
     p.delta_l[o] = dl;
     if (p.eta_par) p.eta_par[o] = ep;
-    if (p.vpar) p.vpar[o] = nf == 10 ? (float)(r.vel[k] / sqrt(RR)) : 0.f;
+    if (p.vpar) p.vpar[o] = nf == 10 ? r.vel[k] : 0.f;
     if (p.flux) store_flux(p, o, i0 + k, dl, ep);
   }
 }
 
-// One walk over the union window for NF fields; src(f, a, b) returns the address of the 8 consecutive z cells of
-// window row (a, b) of field f.  z contraction on pairs of cells (4 FMUL2/FFMA2 per pixel and row), row accumulation
-// with the packed weight (wab, wab): the two halves of acc2 are added only at the end of the walk.
-template <int P, int NF, bool SUMX, class Src>
-__device__ __forceinline__ void walk_window(const SkewerParams& p, const PixelGroup<P>& g, int nxu, int nyu, Src src,
-                                            float2 (&acc2)[NF][P], float (&sx)[P]) {
+// sum of the x weights of every pixel over its window (the third factor of the weight normalisation)
+template <int P>
+__device__ __forceinline__ void sum_x_weights(const SkewerParams& p, const PixelGroup<P>& g, float (&sx)[P]) {
+  const float fdx = (float)p.dx;
+  const float inv_sig2 = (float)(1.0 / (2.0 * p.dx * p.dx));
+#pragma unroll
+  for (int k = 0; k < P; ++k) sx[k] = 0.f;
+#pragma unroll
+  for (int a = 0; a < WU; ++a) {
+    const float ta = (float)a * fdx;          // the same expressions as walk_window: the weights summed are the weights used
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const unsigned m = (unsigned)a - ((g.xlo >> (8 * k)) & 0xffu);
+      const float t = ta + g.tx0[k];
+      sx[k] += (a < g.nxu && m <= 2u * DMAX) ? exp_weight(-t * t * inv_sig2) : 0.f;
+    }
+  }
+}
+
+// One walk over the union window for NF fields.  load(f, a, b, r2) fetches the 8 consecutive z cells of window row
+// (a, b) of field f as four pairs.  Rows 0..6 of every window plane are walked unconditionally (one straight line of
+// code: the loads of a row are issued under the arithmetic of the one before), row 7 only when some pixel of the warp
+// has it in its window (nyu == 8).  z contraction on pairs of cells (4 FMUL2/FFMA2 per pixel and row); rows are
+// accumulated per plane with the y weight as the broadcast operand of one FFMA2, the plane then enters the running sum
+// with its x weight -- no per-row weight product.  The two halves of every accumulator are added at the end of the walk.
+template <int P, int NF, class Load>
+__device__ __forceinline__ void walk_window(const SkewerParams& p, const PixelGroup<P>& g, int nxu, int nyu, Load load,
+                                            float2 (&acc2)[NF][P]) {
   const float fdx = (float)p.dx;
   const float inv_sig2 = (float)(1.0 / (2.0 * p.dx * p.dx));
 #pragma unroll
   for (int f = 0; f < NF; ++f)
 #pragma unroll
     for (int k = 0; k < P; ++k) acc2[f][k] = make_float2(0.f, 0.f);
-  if (SUMX) {
-#pragma unroll
-    for (int k = 0; k < P; ++k) sx[k] = 0.f;
-  }
 #pragma unroll 1
   for (int a = 0; a < nxu; ++a) {
     float wxa[P];
+    const float ta = (float)a * fdx;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const int m = a - DMAX - g.dix[k];                      // cell offset from pixel k's own cell
-      const float t = m * fdx + g.ox[k];
-      wxa[k] = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
-      if (SUMX) sx[k] += wxa[k];
+      const unsigned m = (unsigned)a - ((g.xlo >> (8 * k)) & 0xffu);      // plane a is inside pixel k's window iff m <= 6
+      const float t = ta + g.tx0[k];
+      wxa[k] = m <= 2u * DMAX ? exp_weight(-t * t * inv_sig2) : 0.f;
     }
+    float2 pl2[NF][P];                         // this plane: sum over its rows of wy * (z contraction)
+    auto row = [&](int b, bool first) {
 #pragma unroll
-    for (int b = 0; b < WU; ++b) {
-      if (b < nyu) {
-        float2 wab[P];
+      for (int f = 0; f < NF; ++f) {
+        float2 r2[WU / 2];
+        load(f, a, b, r2);
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-          const float w = wxa[k] * g.wy[k][b];
-          wab[k] = make_float2(w, w);
-        }
+          float2 s2 = fmul2(g.wz2[k][0], r2[0]);
 #pragma unroll
-        for (int f = 0; f < NF; ++f) {
-          const float* __restrict__ row = src(f, a, b);
-          float2 r2[WU / 2];
-#pragma unroll
-          for (int j = 0; j < WU / 2; ++j) r2[j] = make_float2(row[2 * j], row[2 * j + 1]);
-#pragma unroll
-          for (int k = 0; k < P; ++k) {
-            float2 s2 = fmul2(g.wz2[k][0], r2[0]);
-#pragma unroll
-            for (int j = 1; j < WU / 2; ++j) s2 = ffma2(g.wz2[k][j], r2[j], s2);
-            acc2[f][k] = ffma2(wab[k], s2, acc2[f][k]);
-          }
+          for (int j = 1; j < WU / 2; ++j) s2 = ffma2(g.wz2[k][j], r2[j], s2);
+          const float w = (k & 1) ? g.wy2[k / 2][b].y : g.wy2[k / 2][b].x;
+          pl2[f][k] = first ? fmul2(make_float2(w, w), s2) : ffma2(make_float2(w, w), s2, pl2[f][k]);
         }
       }
-    }
-  }
-}
-
-// fold the NF fields [f0, f0+NF) of one walk into the running results
-template <int P, int NF>
-__device__ __forceinline__ void fold_fields(const SkewerParams& p, int q, int i0, int f0, const float2 (&acc2)[NF][P],
-                                            const float (&inv_sw)[P], PixelResult<P>& r) {
+    };
 #pragma unroll
-  for (int k = 0; k < P; ++k) {
-    double xv, yv, zv;
-    pixel_xyz<P>(p, q, min(i0 + k, p.npix - 1), xv, yv, zv);
+    for (int b = 0; b < WU - 1; ++b) row(b, b == 0);
+    if (nyu == WU) row(WU - 1, false);
 #pragma unroll
-    for (int f = 0; f < NF; ++f) result_add<P>(r, f0 + f, k, (acc2[f][k].x + acc2[f][k].y) * inv_sw[k], xv, yv, zv);
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+      for (int k = 0; k < P; ++k) acc2[f][k] = ffma2(make_float2(wxa[k], wxa[k]), pl2[f][k], acc2[f][k]);
   }
 }
 
 // ---------------------------------------------------------------- global-memory walk (clamped indices)
-// All segments (list == null: one CTA per 4 segments of a sightline) or the segments the TMA kernel handed back
+// All segments (list == null: one CTA per 4 segments of a sightline) or the segments the staged kernel handed back
 // (list mode: a fixed grid walks list[1 .. list[0]]).
 template <int P>
 __device__ __forceinline__ void global_segment(const SkewerParams& p, int q, int seg) {
   const int lane = threadIdx.x & 31;
   const int i0 = (seg * 32 + lane) * P;
-  if (i0 >= p.npix) return;
+  if (i0 >= p.npix || seg * 32 * P >= p.npix_forest[q]) return;      // beyond the forest: skewers_sentinel_kernel's pixels
   PixelGroup<P> g;
   if (!pixel_group_setup<P>(p, q, i0, g)) return;
   const int nf = p.rsd ? (p.dla ? 10 : 7) : 1;
-  const bool interior = group_interior<P>(p, g);
+  const Direction dir = sightline_direction(p, q);
   const unsigned plane = (unsigned)p.ny * (unsigned)p.nz;
   PixelResult<P> r;
   float inv_sw[P], sx[P];
+  sum_x_weights<P>(p, g, sx);
 #pragma unroll
-  for (int k = 0; k < P; ++k) { r.d0[k] = 0.f; r.eta[k] = 0.0; r.vel[k] = 0.0; inv_sw[k] = 0.f; }
-  // rows are fetched through L1; a window that reaches over the slab gets its indices clamped (documented deviation
-  // from the reference's unchecked gather, include/smk.h), and its 8 z cells are staged in a local array
-  auto run = [&](auto nfc, int f0, auto sumx) {
-    constexpr int NF = decltype(nfc)::value;
-    constexpr bool SUMX = decltype(sumx)::value;
-    float2 acc2[NF][P];
-    if (interior) {
-      const float* base[NF];
+  for (int k = 0; k < P; ++k) {
+    r.d0[k] = 0.f; r.eta[k] = 0.f; r.vel[k] = 0.f;
+    inv_sw[k] = ((g.actmask >> k) & 1) ? 1.0f / (sx[k] * g.syz[k]) : 0.f;
+  }
+  // window indices clamped to the slab (documented deviation from the reference's unchecked gather, include/smk.h;
+  // a no-op for a window inside the slab), rows fetched through L1
+  int lz[WU];
 #pragma unroll
-      for (int f = 0; f < NF; ++f)
-        base[f] = p.f[f0 + f] + ((size_t)(g.bx - DMAX - p.ix0) * plane + (unsigned)(g.by - DMAX) * (unsigned)p.nz + (g.bz - DMAX));
-      walk_window<P, NF, SUMX>(p, g, g.nxu, g.nyu,
-                               [&](int f, int a, int b) { return base[f] + ((size_t)a * plane + (unsigned)b * (unsigned)p.nz); },
-                               acc2, sx);
-    } else {
-      // clamped walk: one row at a time into registers (rare: only at the edges of the box)
-      const float fdx = (float)p.dx;
-      const float inv_sig2 = (float)(1.0 / (2.0 * p.dx * p.dx));
+  for (int c = 0; c < WU; ++c) lz[c] = min(max(g.bz - DMAX + c, 0), p.nz - 1);
+#pragma unroll 1
+  for (int f = 0; f < nf; ++f) {
+    const float* __restrict__ field = p.f[f];
+    float2 acc2[1][P];
+    walk_window<P, 1>(p, g, g.nxu, g.nyu,
+                      [&](int, int a, int b, float2 (&r2)[WU / 2]) {
+                        const int la = min(max(g.bx - DMAX + a - p.ix0, 0), p.nxs - 1);
+                        const int lb = min(max(g.by - DMAX + b, 0), p.ny - 1);
+                        const float* __restrict__ row = field + ((size_t)la * plane + (unsigned)lb * (unsigned)p.nz);
 #pragma unroll
-      for (int f = 0; f < NF; ++f)
-#pragma unroll
-        for (int k = 0; k < P; ++k) acc2[f][k] = make_float2(0.f, 0.f);
-      if (SUMX) {
-#pragma unroll
-        for (int k = 0; k < P; ++k) sx[k] = 0.f;
-      }
-      int lz[WU];
-#pragma unroll
-      for (int c = 0; c < WU; ++c) lz[c] = min(max(g.bz - DMAX + c, 0), p.nz - 1);
-      for (int a = 0; a < g.nxu; ++a) {
-        const int la = min(max(g.bx - DMAX + a - p.ix0, 0), p.nxs - 1);
-        float wxa[P];
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-          const int m = a - DMAX - g.dix[k];
-          const float t = m * fdx + g.ox[k];
-          wxa[k] = (m >= -DMAX && m <= DMAX) ? __expf(-t * t * inv_sig2) : 0.f;
-          if (SUMX) sx[k] += wxa[k];
-        }
-        for (int b = 0; b < g.nyu; ++b) {
-          const int lb = min(max(g.by - DMAX + b, 0), p.ny - 1);
-          const size_t rowo = (size_t)la * plane + (unsigned)lb * (unsigned)p.nz;
-#pragma unroll
-          for (int f = 0; f < NF; ++f) {
-            const float* __restrict__ srcf = p.f[f0 + f] + rowo;
-            float2 r2[WU / 2];
-#pragma unroll
-            for (int j = 0; j < WU / 2; ++j) r2[j] = make_float2(__ldg(srcf + lz[2 * j]), __ldg(srcf + lz[2 * j + 1]));
-#pragma unroll
-            for (int k = 0; k < P; ++k) {
-              // y weights by dynamic index: select with a compile-time unrolled chain
-              float wyb = 0.f;
-#pragma unroll
-              for (int bb = 0; bb < WU; ++bb) wyb = (bb == b) ? g.wy[k][bb] : wyb;
-              const float w = wxa[k] * wyb;
-              float2 s2 = fmul2(g.wz2[k][0], r2[0]);
-#pragma unroll
-              for (int j = 1; j < WU / 2; ++j) s2 = ffma2(g.wz2[k][j], r2[j], s2);
-              acc2[f][k] = ffma2(make_float2(w, w), s2, acc2[f][k]);
-            }
-          }
-        }
-      }
-    }
-    if (SUMX) {
-#pragma unroll
-      for (int k = 0; k < P; ++k) inv_sw[k] = ((g.actmask >> k) & 1) ? 1.0f / (sx[k] * g.syz[k]) : 0.f;
-    }
-    fold_fields<P, NF>(p, q, i0, f0, acc2, inv_sw, r);
-  };
-  using I1 = std::integral_constant<int, 1>;
-  using I2 = std::integral_constant<int, 2>;
-  using T = std::true_type;
-  using F = std::false_type;
-  if (nf == 1) {
-    run(I1{}, 0, T{});
-  } else {
-    run(I2{}, 0, T{});
-    run(I2{}, 2, F{});
-    run(I2{}, 4, F{});
-    if (nf == 10) {
-      run(I2{}, 6, F{});
-      run(I2{}, 8, F{});
-    } else {
-      run(I1{}, 6, F{});
-    }
+                        for (int j = 0; j < WU / 2; ++j) r2[j] = make_float2(__ldg(row + lz[2 * j]), __ldg(row + lz[2 * j + 1]));
+                      },
+                      acc2);
+    fold_field<P>(f, field_coefficient(dir, f), acc2[0], inv_sw, r);
   }
   result_store<P>(p, q, i0, g.actmask, nf, r);
 }
 
 template <int P>
-__global__ void __launch_bounds__(128, 3) skewers_multi_kernel(const __grid_constant__ SkewerParams p) {
+__global__ void __launch_bounds__(128, 2) skewers_multi_kernel(const __grid_constant__ SkewerParams p) {
   const int warp = threadIdx.x >> 5;
   if (p.list == nullptr) {
     const long long s = (long long)blockIdx.x * 4 + warp;
@@ -545,45 +552,67 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// 3-D box load: coordinates (z, y, x) in elements, any alignment; out-of-range elements arrive as zeros
+// 3-D box load: coordinates (z, y, x) in elements, z a multiple of 4 (16 bytes); out-of-range elements arrive as zeros
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+// 8 consecutive floats of shared memory at a 32-bit shared address (4-byte aligned): explicit ld.shared with
+// immediate offsets, so that the address arithmetic stays one add per row
+__device__ __forceinline__ void lds_row8(uint32_t addr, float2 (&r2)[WU / 2]) {
+  static_assert(WU == 8, "eight cells per window row");
+  asm volatile("ld.shared.f32 %0, [%8];\n\tld.shared.f32 %1, [%8+4];\n\tld.shared.f32 %2, [%8+8];\n\t"
+               "ld.shared.f32 %3, [%8+12];\n\tld.shared.f32 %4, [%8+16];\n\tld.shared.f32 %5, [%8+20];\n\t"
+               "ld.shared.f32 %6, [%8+24];\n\tld.shared.f32 %7, [%8+28];"
+               : "=f"(r2[0].x), "=f"(r2[0].y), "=f"(r2[1].x), "=f"(r2[1].y), "=f"(r2[2].x), "=f"(r2[2].y), "=f"(r2[3].x),
+                 "=f"(r2[3].y)
+               : "r"(addr));
+}
 
-// NW warps per CTA, each on its own segment of 32*P pixels with its own box and mbarrier (no CTA-wide barrier after
-// the set-up); NFG fields staged and walked together.
+// Owned pixels of segments that lie entirely beyond the forest (make_spectra.py:99-101: delta_l = -1e6, eta_par =
+// v_par = 0, and F of that): the gather kernels leave such segments at once, this kernel writes their sentinels.
+// SEG = pixels per segment of the gather that follows (the segment that holds the end of the forest is the gather's).
+__global__ void __launch_bounds__(256) skewers_sentinel_kernel(const __grid_constant__ SkewerParams p, int seg_pixels,
+                                                               int chunks) {
+  const int q = blockIdx.x / chunks;
+  const int i = (blockIdx.x - q * chunks) * 256 + threadIdx.x;
+  const int nfor = p.npix_forest[q];
+  const int start = (nfor + seg_pixels - 1) / seg_pixels * seg_pixels;
+  if (i < start || i >= p.npix) return;
+  const double xv = p.rvec[i] * p.qso[4 * q] / p.qso[4 * q + 3];       // make_spectra.py:443-448
+  if (!(xv > p.xmin) || !(xv <= p.xmax)) return;
+  const size_t o = (size_t)q * p.npix + i;
+  p.delta_l[o] = -1000000.f;
+  if (p.eta_par) p.eta_par[o] = 0.f;
+  if (p.vpar) p.vpar[o] = 0.f;
+  if (p.flux) store_flux(p, o, i, -1000000.f, 0.f);
+}
+
+// One warp per CTA (NW == 1; the code is written for any NW), each on its own segment of 32*P pixels with its own
+// boxes and mbarriers.  NFG fields are staged and walked together; the boxes of the next stage are in flight while the
+// current ones are walked (two buffers, one mbarrier each).
 template <int P, int NFG, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) skewers_tma_kernel(const __grid_constant__ SkewerTmaParams t) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const SkewerParams& p = t.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* const box = reinterpret_cast<float*>(smraw) + (size_t)warp * NFG * t.box_elems;
-  const uint32_t bar = smem_u32(smraw + (size_t)NW * NFG * t.box_elems * sizeof(float)) + 8u * warp;
-  if (lane == 0) mbar_init(bar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncwarp();
   const long long s = (long long)blockIdx.x * NW + warp;
   if (s >= (long long)p.nqso * p.nseg) return;
   const int q = (int)(s / p.nseg), seg = (int)(s - (long long)q * p.nseg);
+  if (seg * 32 * P >= p.npix_forest[q]) return;          // beyond the forest: skewers_sentinel_kernel's pixels
+  const uint32_t stage_bytes = (uint32_t)NFG * t.box_elems * 4u;
+  const uint32_t box = smem_u32(smraw) + (uint32_t)warp * 2u * stage_bytes;
+  const uint32_t bar = smem_u32(smraw) + (uint32_t)NW * 2u * stage_bytes + 16u * warp;
+  if (lane == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
   const int i0 = (seg * 32 + lane) * P;
   PixelGroup<P> g;
   const bool act = (i0 < p.npix) && pixel_group_setup<P>(p, q, i0, g);
   if (!__any_sync(0xffffffffu, act)) return;
-  if (!act) {                       // idle lane of a live warp: zero weights, window at the box origin
-    g.actmask = 0;
-    g.nxu = g.nyu = 2 * DMAX + 1;
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-      g.dix[k] = 100; g.ox[k] = 0.f; g.syz[k] = 1.f;
-#pragma unroll
-      for (int c = 0; c < WU; ++c) g.wy[k][c] = 0.f;
-#pragma unroll
-      for (int j = 0; j < WU / 2; ++j) g.wz2[k][j] = make_float2(0.f, 0.f);
-    }
-  }
+  if (!act) pixel_group_idle<P>(g);
   // the box of the warp: lowest window corner of any live lane; every live lane's 8 x 8 x 8 read must fit into it and
   // every window must lie inside the slab (TMA fills what is outside the tensor with zeros, which only ever meet the
   // zero weights of the 8th row / plane / cell)
@@ -591,61 +620,62 @@ __global__ void __launch_bounds__(NW * 32, MINB) skewers_tma_kernel(const __grid
   const int x0 = __reduce_min_sync(0xffffffffu, act ? g.bx : BIG), x1 = __reduce_max_sync(0xffffffffu, act ? g.bx : -BIG);
   const int y0 = __reduce_min_sync(0xffffffffu, act ? g.by : BIG), y1 = __reduce_max_sync(0xffffffffu, act ? g.by : -BIG);
   const int z0 = __reduce_min_sync(0xffffffffu, act ? g.bz : BIG), z1 = __reduce_max_sync(0xffffffffu, act ? g.bz : -BIG);
-  const bool fits = (x1 - x0 + WU <= t.xw) && (y1 - y0 + WU <= t.yw) && (z1 - z0 + WU <= t.zl);
+  // TMA wants the box to start on a 16-byte boundary along the contiguous axis (measured: an innermost coordinate that
+  // is not a multiple of 4 floats raises "illegal instruction", tools/micro/tma_box_test.cu): round the z origin down
+  const int zb = (z0 - DMAX) & ~3;
+  const bool fits = (x1 - x0 + WU <= t.xw) && (y1 - y0 + WU <= t.yw) && (z1 - DMAX + WU - zb <= t.zl);
   const bool inside = __all_sync(0xffffffffu, !act || group_interior<P>(p, g));
   if (!fits || !inside) {           // hand the segment back to the global-memory kernel
     if (lane == 0) t.handback[1 + atomicAdd(t.handback, 1)] = (int)s;
     return;
   }
   const int nxu = __reduce_max_sync(0xffffffffu, g.nxu), nyu = __reduce_max_sync(0xffffffffu, g.nyu);
-  const int ywzl = t.yw * t.zl;
-  const int rowbase = act ? ((g.bx - x0) * t.yw + (g.by - y0)) * t.zl + (g.bz - z0) : 0;
+  const uint32_t row_bytes = (uint32_t)t.zl * 4u, plane_bytes = (uint32_t)(t.yw * t.zl) * 4u;
+  const uint32_t field_bytes = (uint32_t)t.box_elems * 4u;
+  const uint32_t mine = act ? (uint32_t)(((g.bx - x0) * t.yw + (g.by - y0)) * t.zl + (g.bz - DMAX - zb)) * 4u : 0u;
   const int nf = p.rsd ? (p.dla ? 10 : 7) : 1;
+  const uint32_t box_bytes = (uint32_t)(t.xw * t.yw * t.zl) * (uint32_t)sizeof(float);
+  // a stage = the boxes of fields [f0, f0 + NFG) (a last stage that is not full loads its last field again)
+  auto issue = [&](int f0, int buf) {
+    if (lane == 0) {
+      mbar_expect_tx(bar + 8u * buf, NFG * box_bytes);
+#pragma unroll
+      for (int f = 0; f < NFG; ++f)
+        tma_load_3d(box + buf * stage_bytes + f * field_bytes, &t.map[min(f0 + f, nf - 1)], zb, y0 - DMAX, x0 - DMAX - p.ix0,
+                    bar + 8u * buf);
+    }
+  };
+  issue(0, 0);                      // in flight under the rest of the set-up
+  const Direction dir = sightline_direction(p, q);
   PixelResult<P> r;
   float inv_sw[P], sx[P];
+  sum_x_weights<P>(p, g, sx);
 #pragma unroll
-  for (int k = 0; k < P; ++k) { r.d0[k] = 0.f; r.eta[k] = 0.0; r.vel[k] = 0.0; inv_sw[k] = 0.f; }
-  uint32_t parity = 0;
-  const uint32_t box_bytes = (uint32_t)(t.xw * t.yw * t.zl) * (uint32_t)sizeof(float);
-  const float* const mine = box + rowbase;
-  auto stage = [&](auto nfc, int f0, auto sumx) {
-    constexpr int NF = decltype(nfc)::value;
-    constexpr bool SUMX = decltype(sumx)::value;
-    if (lane == 0) {
-      mbar_expect_tx(bar, NF * box_bytes);
+  for (int k = 0; k < P; ++k) {
+    r.d0[k] = 0.f; r.eta[k] = 0.f; r.vel[k] = 0.f;
+    inv_sw[k] = ((g.actmask >> k) & 1) ? 1.0f / (sx[k] * g.syz[k]) : 0.f;
+  }
+  uint32_t parity = 0;              // bit b: phase of buffer b's mbarrier
+  // ONE copy of the walk in the instruction stream: the warps of an SM are at different stages, and separate copies per
+  // stage thrashed the instruction cache (profiles/README.md)
+#pragma unroll 1
+  for (int f0 = 0, it = 0; f0 < nf; f0 += NFG, ++it) {
+    const int buf = it & 1;
+    // the other buffer was last read by the walk before this one (every lane passed its __syncwarp): refill it now
+    if (f0 + NFG < nf) issue(f0 + NFG, buf ^ 1);
+    mbar_wait(bar + 8u * buf, (parity >> buf) & 1u);
+    parity ^= 1u << buf;
+    const uint32_t base = box + buf * stage_bytes + mine;
+    float2 acc2[NFG][P];
+    walk_window<P, NFG>(p, g, nxu, nyu,
+                        [&](int f, int a, int b, float2 (&r2)[WU / 2]) {
+                          lds_row8(base + f * field_bytes + a * plane_bytes + b * row_bytes, r2);
+                        },
+                        acc2);
+    __syncwarp();                   // every lane is done with this buffer before the stage after next overwrites it
 #pragma unroll
-      for (int f = 0; f < NF; ++f)
-        tma_load_3d(smem_u32(box + (size_t)f * t.box_elems), &t.map[f0 + f], z0 - DMAX, y0 - DMAX, x0 - DMAX - p.ix0, bar);
-    }
-    mbar_wait(bar, parity);
-    parity ^= 1u;
-    float2 acc2[NF][P];
-    walk_window<P, NF, SUMX>(p, g, nxu, nyu,
-                             [&](int f, int a, int b) { return mine + (f * t.box_elems + a * ywzl + b * t.zl); }, acc2, sx);
-    __syncwarp();                   // every lane is done with the boxes before the next stage overwrites them
-    if (SUMX) {
-#pragma unroll
-      for (int k = 0; k < P; ++k) inv_sw[k] = ((g.actmask >> k) & 1) ? 1.0f / (sx[k] * g.syz[k]) : 0.f;
-    }
-    if (act) fold_fields<P, NF>(p, q, i0, f0, acc2, inv_sw, r);
-  };
-  using I1 = std::integral_constant<int, 1>;
-  using I2 = std::integral_constant<int, 2>;
-  using T = std::true_type;
-  using F = std::false_type;
-  static_assert(NFG == 2, "stages of two fields");
-  if (nf == 1) {
-    stage(I1{}, 0, T{});
-  } else {
-    stage(I2{}, 0, T{});
-    stage(I2{}, 2, F{});
-    stage(I2{}, 4, F{});
-    if (nf == 10) {
-      stage(I2{}, 6, F{});
-      stage(I2{}, 8, F{});
-    } else {
-      stage(I1{}, 6, F{});
-    }
+    for (int f = 0; f < NFG; ++f)
+      if (f == 0 || f0 + f < nf) fold_field<P>(f0 + f, field_coefficient(dir, f0 + f), acc2[f], inv_sw, r);
   }
   if (act) result_store<P>(p, q, i0, g.actmask, nf, r);
 }
@@ -670,33 +700,45 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-constexpr int SKEW_P = 4, SKEW_NFG = 2, SKEW_NW = 4, SKEW_MINB = 3;
-
 // bookkeeping of the calling thread's last gather (smk_skewers_stats)
 struct LastGather { const int* handback = nullptr; long long nsegs = 0; int xw = 0, yw = 0, zl = 0; cudaStream_t st = nullptr; };
 static thread_local LastGather g_last;
+
 constexpr int SKEW_BOX_MAX = 16;          // largest staged box extent along x / y (cells)
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-// Staged launch.  Returns SMK_ERR_UNSUPPORTED (without touching the error string) when the inputs do not meet TMA's
-// alignment rules, in which case the caller uses the global-memory kernel for everything.
-static int launch_staged(smk_ctx* ctx, const smk_geom* g, const SkewerParams& p, cudaStream_t st) {
+static int launch_sentinels(const SkewerParams& p, int seg_pixels, cudaStream_t st) {
+  const int chunks = (p.npix + 255) / 256;
+  const long long nblocks = (long long)p.nqso * chunks;
+  if (nblocks > 2147483647LL) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
+  skewers_sentinel_kernel<<<(unsigned)nblocks, 256, 0, st>>>(p, seg_pixels, chunks);
+  SMK_CUDA_OK(cudaGetLastError());
+  return SMK_OK;
+}
+
+// Staged launch: one warp per CTA, every warp stages its own boxes, so the number of warps an SM holds is set by
+// shared memory (and registers) alone.  Returns SMK_ERR_UNSUPPORTED (without touching the error string) when the
+// inputs do not meet TMA's alignment rules, in which case the caller uses the global-memory kernel for everything.
+template <int P, int NFG, int MINB>
+static int launch_staged(smk_ctx* ctx, const smk_geom* g, SkewerParams p, cudaStream_t st) {
   EncodeTiledFn encode = encode_tiled_fn();
   const int nf = p.rsd ? (p.dla ? 10 : 7) : 1;
   if (!encode || p.nz % 4 != 0) return SMK_ERR_UNSUPPORTED;
   for (int f = 0; f < nf; ++f)
     if ((uintptr_t)p.f[f] & 15) return SMK_ERR_UNSUPPORTED;
+  p.nseg = (p.npix + 32 * P - 1) / (32 * P);
+  p.list = nullptr;
   SkewerTmaParams t{};
   t.p = p;
   // extent of the box a segment of 32*P pixels can need: cells crossed along the axis + the 8-cell union window
-  const double lseg = (32 * SKEW_P - 1) * g->pixel_step;
+  const double lseg = (32 * P - 1) * g->pixel_step;
   auto extent = [&](double dir, double d) { return (int)floor(lseg * fmin(fabs(dir), 1.0) / d) + 1 + WU; };
   const double dirx = g->dir_x_max > 0 ? g->dir_x_max : 0.25, diry = g->dir_y_max > 0 ? g->dir_y_max : 0.25;
   t.xw = extent(dirx, g->dx) < SKEW_BOX_MAX ? extent(dirx, g->dx) : SKEW_BOX_MAX;
   t.yw = extent(diry, g->dy) < SKEW_BOX_MAX ? extent(diry, g->dy) : SKEW_BOX_MAX;
-  t.zl = round_up(extent(1.0, g->dz), 4);                        // rows of whole 16-byte units
-  if (t.xw > p.nxs + 2 * DMAX + 2 || t.zl > 256) return SMK_ERR_UNSUPPORTED;
+  t.zl = round_up(extent(1.0, g->dz) + 3, 4);     // rows of whole 16-byte units, origin rounded down to one (+3)
+  if (t.zl > 256) return SMK_ERR_UNSUPPORTED;
   t.box_elems = round_up(t.xw * t.yw * t.zl, 32);
   for (int f = 0; f < nf; ++f) {
     const cuuint64_t dims[3] = {(cuuint64_t)p.nz, (cuuint64_t)p.ny, (cuuint64_t)p.nxs};
@@ -713,17 +755,18 @@ static int launch_staged(smk_ctx* ctx, const smk_geom* g, const SkewerParams& p,
   t.handback = (int*)smk_ctx_scratch(ctx, (size_t)(nsegs + 1) * sizeof(int));
   if (!t.handback) return SMK_ERR_CUDA;
   SMK_CUDA_OK(cudaMemsetAsync(t.handback, 0, sizeof(int), st));
-  auto kern = skewers_tma_kernel<SKEW_P, SKEW_NFG, SKEW_NW, SKEW_MINB>;
-  const size_t smem = (size_t)SKEW_NW * SKEW_NFG * t.box_elems * sizeof(float) + SKEW_NW * 8;
+  { const int rc = launch_sentinels(p, 32 * P, st); if (rc) return rc; }
+  auto kern = skewers_tma_kernel<P, NFG, 1, MINB>;
+  const size_t smem = (size_t)2 * NFG * t.box_elems * sizeof(float) + 16;      // two stages of NFG boxes + two mbarriers
   if (smem > 227 * 1024) return SMK_ERR_UNSUPPORTED;
   SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)((nsegs + SKEW_NW - 1) / SKEW_NW), SKEW_NW * 32, smem, st>>>(t);
+  kern<<<(unsigned)nsegs, 32, smem, st>>>(t);
   SMK_CUDA_OK(cudaGetLastError());
   g_last.handback = t.handback; g_last.nsegs = nsegs; g_last.xw = t.xw; g_last.yw = t.yw; g_last.zl = t.zl; g_last.st = st;
   // the segments handed back (box edges, oblique segments): fixed grid over the list
   SkewerParams pl = p;
   pl.list = t.handback;
-  skewers_multi_kernel<SKEW_P><<<148 * 3, 128, 0, st>>>(pl);
+  skewers_multi_kernel<P><<<148 * 2, 128, 0, st>>>(pl);
   SMK_CUDA_OK(cudaGetLastError());
   return SMK_OK;
 }
@@ -737,18 +780,27 @@ int launch_skewers(smk_ctx* ctx, const smk_geom* g, SkewerParams& p, int dmax, d
   const int NT = 128;
   // register-blocked kernels: valid while P consecutive pixels cannot cross two cell boundaries on any axis
   const double cell = fmin(p.dx, fmin(p.dy, p.dz));
-  const bool multi = (dmax == DMAX) && pixel_step > 0 && (SKEW_P - 1) * pixel_step < cell;
-  if (multi) {
+  auto blocked_ok = [&](int P) { return (dmax == DMAX) && pixel_step > 0 && (P - 1) * pixel_step < cell; };
+  if (blocked_ok(4)) {
     if (fused) *fused = true;
-    p.nseg = (p.npix + 32 * SKEW_P - 1) / (32 * SKEW_P);
-    p.list = nullptr;
     if (staged && ctx) {
-      const int rc = launch_staged(ctx, g, p, st);
+      // experiment switch (pixels per thread x fields per stage); the default is the measured best (profiles/README.md)
+      const char* e = getenv("SMK_SKEW_VARIANT");
+      const int variant = e ? atoi(e) : SMK_SKEW_VARIANT_DEFAULT;
+      int rc = SMK_ERR_UNSUPPORTED;
+      if (variant == 4116) rc = launch_staged<4, 1, 16>(ctx, g, p, st);          // 128 registers, 16 warps
+      else if (variant == 418) rc = launch_staged<4, 1, 8>(ctx, g, p, st);       // 255 registers, 8 warps
+      else if (variant == 428) rc = launch_staged<4, 2, 8>(ctx, g, p, st);
+      else if (variant == 42) rc = launch_staged<4, 2, 12>(ctx, g, p, st);
+      else rc = launch_staged<4, 1, 12>(ctx, g, p, st);                          // 41: 168 registers, 12 warps
       if (rc != SMK_ERR_UNSUPPORTED) return rc;
     }
+    p.nseg = (p.npix + 32 * 4 - 1) / (32 * 4);
+    p.list = nullptr;
     const long long nblocks = ((long long)p.nqso * p.nseg + 3) / 4;
     if (nblocks > 2147483647LL) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
-    skewers_multi_kernel<SKEW_P><<<(unsigned)nblocks, NT, 0, st>>>(p);
+    { const int rc = launch_sentinels(p, 32 * 4, st); if (rc) return rc; }
+    skewers_multi_kernel<4><<<(unsigned)nblocks, NT, 0, st>>>(p);
     SMK_CUDA_OK(cudaGetLastError());
     return SMK_OK;
   }

@@ -118,6 +118,70 @@ static int launch_smallscale_t(const SmallScaleParams& p, cudaStream_t st) {
   return SMK_OK;
 }
 
+// ---- 1-D power spectrum of the rows (py/SaclayMocks/powerspectrum.py:204-238: P1D_1spectrum = |rfft(delta)|^2 DX / n,
+// accumulated over spectra by ComputeP1D).  One CTA per row: the nfft pixels starting at first[q] (rows with fewer than
+// nfft valid pixels are skipped), optionally turned into a contrast v / mean[q] - 1, nfft-point r2c in shared memory
+// (the half-length complex FFT of smallscale_kernel), then sum P and sum P^2 per wavenumber with float64 atomics.
+struct P1DParams {
+  int nqso, npix;
+  const float* rows;       // [nqso][npix]
+  const int* first;        // [nqso] first pixel of the window (null: 0)
+  const int* nvalid;       // [nqso] valid pixels from `first` on (null: npix)
+  const float* mean;       // [nqso] (null: the rows are used as they are)
+  float scale;             // DX / nfft
+  double* sums;            // [2][nfft/2+1]
+  unsigned long long* nused;
+  const float2* tw;
+};
+
+template <int M>
+__global__ void __launch_bounds__(M >= 2048 ? 512 : (M >= 512 ? 256 : 64)) p1d_kernel(P1DParams p) {
+  using P = typename PlanFor<M>::type;
+  constexpr int NT = M >= 2048 ? 512 : (M >= 512 ? 256 : 64);
+  extern __shared__ float2 sm[];   // [M + M/16 + 1]
+  const int q = blockIdx.x;
+  const int nfft = 2 * M;
+  const int i0 = p.first ? p.first[q] : 0;
+  const int nv = p.nvalid ? p.nvalid[q] : p.npix - i0;
+  if (i0 < 0 || nv < nfft || i0 + nfft > p.npix) return;
+  auto ld = [&](int, int pos, int, int) { return sm[ss_idx(pos)]; };
+  auto st = [&](int, int pos, float2 val) { sm[ss_idx(pos)] = val; };
+  const float* row = p.rows + (size_t)q * p.npix + i0;
+  const float inv_mean = p.mean ? 1.0f / p.mean[q] : 1.0f, off = p.mean ? 1.0f : 0.0f;
+  for (int n = threadIdx.x; n < M; n += NT)
+    sm[ss_idx(n)] = make_float2(row[2 * n] * inv_mean - off, row[2 * n + 1] * inv_mean - off);
+  __syncthreads();
+  ss_fft<P, 0, false, NT>(ld, st, p.tw);
+  for (int k = threadIdx.x; k <= M / 2; k += NT) {
+    float2 a = sm[ss_idx(k)], b = (k == 0) ? a : sm[ss_idx(M - k)];
+    float2 w = __ldg(p.tw + k);
+    float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+    float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
+    float2 t = cmul(w, d);
+    float2 mit = make_float2(t.y, -t.x);
+    float2 xk = cadd(e, mit);                                       // X[k]
+    float2 xm = make_float2(e.x - mit.x, -e.y + mit.y);             // X[M-k]
+    const double pk = (double)((xk.x * xk.x + xk.y * xk.y) * p.scale);
+    atomicAdd(p.sums + k, pk);
+    atomicAdd(p.sums + (M + 1) + k, pk * pk);
+    if (k != M - k) {
+      const double pm = (double)((xm.x * xm.x + xm.y * xm.y) * p.scale);
+      atomicAdd(p.sums + (M - k), pm);
+      atomicAdd(p.sums + (M + 1) + (M - k), pm * pm);
+    }
+  }
+  if (threadIdx.x == 0) atomicAdd(p.nused, 1ULL);
+}
+
+template <int M>
+static int launch_p1d_t(const P1DParams& p, cudaStream_t st) {
+  constexpr int NT = M >= 2048 ? 512 : (M >= 512 ? 256 : 64);
+  size_t smem = (size_t)(M + M / 16 + 1) * sizeof(float2);
+  p1d_kernel<M><<<p.nqso, NT, smem, st>>>(p);
+  SMK_CUDA_OK(cudaGetLastError());
+  return SMK_OK;
+}
+
 __global__ void fgpa_kernel(size_t n, int npix, const float* __restrict__ delta_l, const float* __restrict__ delta_s,
                             const float* __restrict__ eta, const float* __restrict__ G, const float* __restrict__ a,
                             const float* __restrict__ b, const float* __restrict__ c, float* __restrict__ flux) {
@@ -186,6 +250,27 @@ extern "C" int smk_smallscale(smk_ctx* ctx, int nqso, int nfft, int npix, const 
     case 8192: return launch_smallscale_t<4096>(p, st);
   }
   set_error("smk_smallscale: nfft must be a power of two in [256, 8192]");
+  return SMK_ERR_UNSUPPORTED;
+}
+
+extern "C" int smk_p1d(smk_ctx* ctx, int nqso, int npix, int nfft, const float* rows, const int* first, const int* nvalid,
+                       const float* mean, double pixel, double* sums, unsigned long long* nused) {
+  using namespace smk;
+  if (nqso == 0) return SMK_OK;
+  if (!rows || !sums || !nused || nfft > npix || pixel <= 0) { set_error("smk_p1d: bad argument"); return SMK_ERR_ARG; }
+  P1DParams p{nqso, npix, rows, first, nvalid, mean, (float)(pixel / nfft), sums, nused, nullptr};
+  int rc = smk_tw1d(nfft, &p.tw);
+  if (rc) return rc;
+  cudaStream_t st = smk_ctx_stream(ctx);
+  switch (nfft) {
+    case 256: return launch_p1d_t<128>(p, st);
+    case 512: return launch_p1d_t<256>(p, st);
+    case 1024: return launch_p1d_t<512>(p, st);
+    case 2048: return launch_p1d_t<1024>(p, st);
+    case 4096: return launch_p1d_t<2048>(p, st);
+    case 8192: return launch_p1d_t<4096>(p, st);
+  }
+  set_error("smk_p1d: nfft must be a power of two in [256, 8192]");
   return SMK_ERR_UNSUPPORTED;
 }
 

@@ -225,3 +225,40 @@ class FGPA(object):
         _lib.check(self.lib.smk_fgpa(self.ctx.handle(), nq, npix, _ptr(delta_l), _ptr(delta_s), _ptr(eta_par), _ptr(self.G),
                                      _ptr(self.a), _ptr(self.b), _ptr(self.c), _ptr(F)))
         return F
+
+
+class P1DEstimator(object):
+    """GPU ComputeP1D (py/SaclayMocks/powerspectrum.py:204-238): mean of P1D_1spectrum over the rows, on windows of
+    nfft pixels.  add() accumulates on the device; result() returns (k [h/Mpc], P1D [Mpc/h], error of the mean, rows)."""
+
+    def __init__(self, nfft, pixel, device=None):
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.ctx = _lib.StreamCtx(self.device)
+        self.nfft, self.pixel = int(nfft), float(pixel)
+        self.sums = torch.zeros((2, self.nfft // 2 + 1), dtype=torch.float64, device=self.device)
+        self.nused = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def add(self, rows, first=None, nvalid=None, mean=None):
+        """rows: device float32 [nqso, npix]; first / nvalid: per-row window start and valid length (int32 device tensors
+        or arrays, optional); mean: per-row mean for the contrast rows / mean - 1 (optional)."""
+        assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous()
+        nq, npix = rows.shape
+        i32 = lambda v: None if v is None else torch.as_tensor(np.asarray(v.cpu() if torch.is_tensor(v) else v, dtype=np.int32),
+                                                               device=self.device)
+        f32 = lambda v: None if v is None else torch.as_tensor(np.asarray(v.cpu() if torch.is_tensor(v) else v, dtype=np.float32),
+                                                               device=self.device)
+        first_t, nvalid_t, mean_t = i32(first), i32(nvalid), f32(mean)
+        _lib.check(self.lib.smk_p1d(self.ctx.handle(), nq, npix, self.nfft, _ptr(rows), _ptr(first_t), _ptr(nvalid_t),
+                                    _ptr(mean_t), C.c_double(self.pixel), _ptr(self.sums), _ptr(self.nused)))
+        torch.cuda.current_stream(self.device).synchronize()       # the temporaries above may be released now
+
+    def result(self):
+        n = int(self.nused.item())
+        s = self.sums.cpu().numpy()
+        k = 2 * np.pi * np.fft.rfftfreq(self.nfft) / self.pixel
+        if n == 0:
+            return k, np.zeros_like(k), np.zeros_like(k), 0
+        mean = s[0] / n
+        var = np.maximum(s[1] / n - mean ** 2, 0.0)
+        return k, mean, np.sqrt(var / max(n, 1)), n

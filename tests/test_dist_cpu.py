@@ -68,3 +68,44 @@ def test_slab_exchange_layouts_gloo(tmp_path):
     for r in range(2):
         e1, e2, e3 = open(out + ".%d" % r).read().split()
         assert float(e1) < 1e-4 and float(e2) < 1e-5 and int(e3) == 0
+
+
+def _gather_worker(rank, world, port, out):
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from saclaymocks_b200 import slab
+    rng = np.random.default_rng(1)
+    LX, n = 100.0, 60
+    xyzr = np.stack([rng.uniform(-48, 48, n), rng.uniform(-40, 40, n), rng.uniform(300, 400, n),
+                     rng.uniform(420, 500, n)], 1)
+    rvec = 200.0 + 0.2 * np.arange(1200)
+    X = xyzr[:, 0:1] * rvec[None, :] / xyzr[:, 3:4]
+    truth = np.sin(X) + np.arange(n)[:, None]                       # what a single process would compute per pixel
+    xmin, xmax = slab.x_bounds(rank, world, LX)
+    mine = np.where(slab.touching(xyzr, rvec[0], rvec[-1], xmin, xmax))[0]
+    rows = np.full((len(mine), len(rvec)), np.nan, dtype=np.float32)
+    own = (X[mine] > xmin) & (X[mine] <= xmax)
+    rows[own] = truth[mine][own]
+    plan = slab.row_gather_plan(xyzr, rvec[0], rvec[-1], world, LX, rank)
+    got = slab.exchange_rows(torch.from_numpy(rows), plan).numpy()
+    home = plan["home_qso"]
+    inside = (X[home] > -LX / 2) & (X[home] <= LX / 2)
+    ok = np.array_equal(np.isnan(got), ~inside) and np.allclose(got[inside], np.float32(truth[home][inside]))
+    cnt = torch.tensor([len(home)])
+    dist.all_reduce(cnt)
+    with open(out + ".%d" % rank, "w") as f:
+        f.write("%d %d" % (int(ok), int(cnt.item())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_rows_gather_to_home_rank_gloo(tmp_path, world):
+    """Sharded spectra rows -> complete rows on the home rank (slab.row_gather_plan / exchange_rows): every pixel inside
+    the box arrives exactly once, pixels outside stay NaN, every quasar has exactly one home."""
+    out = str(tmp_path / "g")
+    mp.spawn(_gather_worker, args=(world, 29741 + world, out), nprocs=world, join=True)
+    for r in range(world):
+        ok, cnt = open(out + ".%d" % r).read().split()
+        assert int(ok) == 1 and int(cnt) == 60

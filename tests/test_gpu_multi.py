@@ -77,6 +77,26 @@ def _worker(rank, world, port, shape, dcell, out, p2p, xsms=0):
         npieces += 1
     errs["skewers"] = worst
     errs["npieces"] = npieces
+    # complete rows on the home rank (ChunkPipeline.gather_rows): every piece of every slice of this rank's quasars
+    rows = pipe.gather_rows()
+    gdl, gep = rows["delta_l"].cpu().numpy(), rows["eta_par"].cpu().numpy()
+    home = list(rows["index"])
+    worst_g, npx_g = 0.0, 0
+    if home:
+        qh = q[np.asarray(home)]
+        for s_ in range(world):
+            files_ = [qh[:0]] * world
+            files_[min(s_, world - 1) if s_ < world // 2 else world // 2] = qh     # a file the half-selection keeps
+            for p in osp.make_spectra_slice(og, boxes, files_, s_, world, 190.0, 0.0):
+                idx = np.searchsorted(lam32, p["lam"])
+                row = home.index(p["id"])
+                m = p["delta_l"] > -1e5
+                if m.any():
+                    worst_g = max(worst_g, float(np.max(np.abs(gdl[row, idx][m] - p["delta_l"][m]))),
+                                  float(np.max(np.abs(gep[row, idx] - p["eta_par"]))))
+                    npx_g += int(m.sum())
+    errs["gathered"] = worst_g
+    errs["gathered_px"] = npx_g
     import json
     json.dump({k: float(v) for k, v in errs.items()}, open(out + ".%d" % rank, "w"))
     dist.destroy_process_group()
@@ -104,17 +124,21 @@ def test_sharded_pipeline_matches_oracle(tmp_path, world, shape, p2p, xsms):
     out = str(tmp_path / "res")
     port = 29600 + 20 * CASES.index((world, shape, p2p, xsms))
     mp.spawn(_worker, args=(world, port, shape, 3364.0 / shape[2], out, p2p, xsms), nprocs=world, join=True)
-    pieces = 0
+    pieces = gathered = 0
     for r in range(world):
         import json
         errs = json.load(open(out + ".%d" % r))
         for k, v in errs.items():
             if k == "npieces":
                 pieces += v
+            elif k == "gathered_px":
+                gathered += v
+            elif k == "gathered":
+                assert v < 1e-5, (r, k, v)
             elif k == "skewers":
                 assert v < 1e-5, (r, k, v)
             elif k == "sigma":
                 assert v < 1e-4, (r, k, v)
             else:
                 assert v < 1e-5, (r, k, v)
-    assert pieces > 0
+    assert pieces > 0 and gathered > 1000

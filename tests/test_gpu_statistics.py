@@ -119,3 +119,101 @@ def test_gpu_pk_estimator_matches_independent_estimator(cuda):
         truth = (np.maximum(pk.spline("P0")(k[m].astype(np.float64)), 0) * mult[m]).sum() / mult[m].sum()
         assert abs(P[i] / truth - 1) < 5.5 / np.sqrt(nmodes[i]), i
     bs.close()
+
+
+def test_gpu_p1d_estimator_matches_numpy(cuda):
+    """smk_p1d (GPU P1D_1spectrum averaged like ComputeP1D, powerspectrum.py:204-238) against numpy's rfft on the same
+    windows: plain rows, windows with an offset / too-short rows skipped, and the contrast F / <F> - 1."""
+    from saclaymocks_b200 import spectra as sp
+    rng = np.random.default_rng(11)
+    nq, npix, pix = 64, 6524, 0.2
+    rows = rng.standard_normal((nq, npix)).astype(np.float32)
+    rows_d = torch.as_tensor(rows, device=cuda)
+    for nfft in (256, 2048, 4096):
+        first = rng.integers(0, 200, nq).astype(np.int32)
+        nvalid = rng.integers(nfft - 300, npix - 200, nq).astype(np.int32)
+        mean = (1.0 + 0.2 * rng.random(nq)).astype(np.float32)
+        est = sp.P1DEstimator(nfft, pix, device=cuda)
+        est.add(rows_d, first=first, nvalid=nvalid, mean=mean)
+        k, p1d, err, n = est.result()
+        use = [q for q in range(nq) if nvalid[q] >= nfft]
+        assert n == len(use) and 0 < n < nq
+        ref = np.array([np.abs(np.fft.rfft(rows[q, first[q]:first[q] + nfft].astype(np.float64) / mean[q] - 1)) ** 2
+                        * pix / nfft for q in use])
+        assert np.allclose(k, np.fft.rfftfreq(nfft) * 2 * np.pi / pix)
+        assert np.max(np.abs(p1d / ref.mean(axis=0) - 1)) < 2e-5
+        assert np.max(np.abs(err / (ref.std(axis=0) / np.sqrt(n)) - 1)) < 1e-3
+    est = sp.P1DEstimator(4096, pix, device=cuda)          # two calls accumulate
+    est.add(rows_d[:30])
+    est.add(rows_d[30:])
+    assert est.result()[3] == nq
+    ref = (np.abs(np.fft.rfft(rows[:, :4096].astype(np.float64), axis=1)) ** 2 * pix / 4096).mean(axis=0)
+    assert np.max(np.abs(est.result()[1] / ref - 1)) < 2e-5
+
+
+def test_p1d_of_flux_against_cpu_oracle_on_the_same_boxes(cuda):
+    """Acceptance of the end product: P1D of delta_F = F / <F> - 1 from the GPU chain (Philox boxes -> skewers ->
+    delta_s -> FGPA -> smk_p1d) against the CPU oracle's chain run on the SAME boxes and the same small-scale noise
+    (oracle ReadSpec + small-scale field + fgpa, numpy P1D_1spectrum): the two P1D agree to 1e-4 per wavenumber,
+    far inside the mode-count error of either, and the mean transmissions to 1e-6."""
+    from oracle import merge as om
+    from oracle import spectra as osp
+    from saclaymocks_b200 import pk
+    from saclaymocks_b200 import spectra as sp
+    from saclaymocks_b200.boxes import BoxSynth, WEIGHT_OF
+    NX, NY, NZ, dcell = 32, 32, 1536, 2.19
+    bs = BoxSynth(NX, NY, NZ, dcell, device=cuda)
+    W = pk.weight_tables(NX, NY, NZ, dcell)
+    boxk = bs.draw_grf_boxk(seed=17)
+    fields = {"box": bs.synth(boxk, "box", wtable=bs.upload_weights(W["P0"]))[0]}
+    for name in sp.FIELDS[1:]:
+        fields[name] = bs.synth(boxk, name)[0]
+    geom = sp.SkewerGeometry(NX, NY, NZ, dcell)
+    rng = np.random.default_rng(3)
+    nq = 48
+    half = np.degrees(np.arctan((geom.LX / 2 - 4 * dcell) / (geom.R0 + geom.LZ / 2))) * 0.9
+    q = np.zeros(nq, dtype=[("RA", "f4"), ("DEC", "f4"), ("Z_QSO_NO_RSD", "f4"), ("Z_QSO_RSD", "f4"),
+                            ("THING_ID", "i8"), ("HDU", "i4")])
+    q["RA"], q["DEC"] = 190.0 + rng.uniform(-half, half, nq), rng.uniform(-half, half, nq)
+    q["Z_QSO_RSD"] = q["Z_QSO_NO_RSD"] = rng.uniform(3.2, 3.55, nq)
+    q["THING_ID"] = np.arange(nq)
+    xyzr, nfor = sp.qso_lines_of_sight(geom, q["RA"], q["DEC"], q["Z_QSO_RSD"], 190.0, 0.0)
+    eng = sp.SkewerEngine(geom, device=cuda)
+    dl, ep, vp = eng.read_spec(fields, xyzr, nfor)
+    fg = sp.FGPA(geom, zfix=2.4, device=cuda)
+    nfm = fg.forest_count(q["Z_QSO_RSD"])
+    noise = rng.normal(size=(nq, fg.nfft_for(geom.npixeltot)))
+    ds = fg.small_scales(nfm, noise=noise)
+    F = fg.flux(dl, ds, ep)
+    nfft = 4096
+    est = sp.P1DEstimator(nfft, 0.2, device=cuda)
+    meanF = torch.stack([F[i, :nfft].mean() for i in range(nq)])
+    est.add(F, nvalid=nfm.astype(np.int32), mean=meanF)
+    k, p_gpu, err, n = est.result()
+    assert n == nq                                                   # every forest is longer than the window
+    # ---- the CPU oracle on the same boxes
+    boxes = {kf: v.cpu().numpy() for kf, v in fields.items()}
+    og = osp.Geometry(NX, NY, NZ, dcell)
+    lam32 = np.float32(geom.lambda_vec)
+    p1d = om.P1DMissing()
+    z32 = fg.z
+    a, b, c = (getattr(fg, x).cpu().numpy().astype(np.float64) for x in "abc")
+    p_cpu, mean_diff = [], 0.0
+    pieces = {pc["id"]: pc for pc in osp.make_spectra_slice(og, boxes, [q], 0, 1, 190.0, 0.0)}
+    assert len(pieces) == nq
+    for i in range(nq):
+        pc = pieces[i]
+        idx = np.searchsorted(lam32, pc["lam"])
+        assert idx[0] == 0 and len(idx) >= nfft
+        zeff = z32[:nfm[i]].mean()
+        dsc = om.small_scale_field(noise[i], geom.npixeltot, zeff, z32, p1d)
+        Fc = om.fgpa(np.float64(pc["delta_l"][:nfft]) + dsc[:nfft], np.float64(pc["eta_par"][:nfft]), fg.growthf[:nfft],
+                     a[:nfft], b[:nfft], c[:nfft])
+        mean_diff = max(mean_diff, abs(Fc.mean() - float(meanF[i])))
+        p_cpu.append(np.abs(np.fft.rfft(Fc / Fc.mean() - 1)) ** 2 * 0.2 / nfft)
+    p_cpu = np.mean(p_cpu, axis=0)
+    assert mean_diff < 1e-6
+    sel = (k > 0.05) & (k < 10.0)
+    assert np.max(np.abs(p_gpu[sel] / p_cpu[sel] - 1)) < 1e-4
+    assert np.all(err[sel] / p_gpu[sel] > 5e-2)                      # the statistical error is orders of magnitude larger
+    bs.close()
