@@ -299,9 +299,10 @@ template <int M>
 struct ZTraits {
   using P = typename PlanFor<M>::type;
 #ifndef SMK_Z_LINES
-#define SMK_Z_LINES 16   // lines per tile of the z passes (M <= 1024); 8 halves the tile (4 CTAs of 128 threads per SM)
-#endif
-  static constexpr int LINES = (M > 1024) ? 4 : ((M >= 512) ? SMK_Z_LINES : 16);
+#define SMK_Z_LINES 8    // lines per tile of the NZ = 1536 z passes: 8 = four CTAs of 128 threads and 50 KB per SM, whose
+#endif                   // load / transform / store phases interleave better than those of two 16-line CTAs (measured on
+                         // B200, tools/z_lines_check.sh: c2r z 0.787 -> 0.772 ms, r2c z + Philox 1.186 -> 1.147 ms)
+  static constexpr int LINES = (M > 1024) ? 4 : ((M == 768) ? SMK_Z_LINES : 16);
   static constexpr int NT_ = (M % 3 == 0) ? LINES * M / 48 / 32 * 32 : LINES * M / 32;
   static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
   // PERM: two-stage plan R0.R1 with a radix-32 first stage, run without the re-sorting last stage (which would need

@@ -228,6 +228,9 @@ template <int P>
 __device__ __forceinline__ bool pixel_group_setup(const SkewerParams& p, int q, int i0, PixelGroup<P>& g) {
   const int nfor = p.npix_forest[q];
   const double LX = p.dx * p.nx, LY = p.dy * p.ny, LZ = p.dz * p.nz;
+  const double inv_dx = 1.0 / p.dx, inv_dy = 1.0 / p.dy, inv_dz = 1.0 / p.dz;
+  const double R = p.qso[4 * q + 3];
+  const double ux = p.qso[4 * q] / R, uy = p.qso[4 * q + 1] / R, uz = p.qso[4 * q + 2] / R;
   const float inv_sig2 = (float)(1.0 / (2.0 * p.dx * p.dx));
   const float fdy = (float)p.dy, fdz = (float)p.dz;
   g.actmask = 0;
@@ -240,8 +243,21 @@ __device__ __forceinline__ bool pixel_group_setup(const SkewerParams& p, int q, 
     ix[k] = iy[k] = iz[k] = 0;
     g.ox[k] = oy[k] = oz[k] = 0.f;
     if (i >= p.npix) continue;
-    double xv, yv, zv;
-    pixel_xyz<P>(p, q, i, xv, yv, zv);
+    // Pixel position and cell: the reference's expressions are r * X / R and int((x + L/2) / D) (make_spectra.py:443-452,
+    // :47-49).  They are first evaluated with reciprocals (r * (X / R), (x + L/2) * (1 / D): no float64 division per
+    // pixel); the results can differ from the reference's by a few ulp, which changes the cell index or the slab that
+    // owns the pixel only within ~1e-13 of a cell / slab boundary -- anything within 1e-9 of one is re-evaluated with
+    // the reference's own operations, so the integer work stays exactly the reference's.
+    const double r = p.rvec[i];
+    double xv = r * ux, yv = r * uy, zv = r * uz;
+    double cx = (xv + LX / 2) * inv_dx, cy = (yv + LY / 2) * inv_dy, cz = (zv + LZ / 2 - p.r0) * inv_dz;
+    const double fx = cx - floor(cx), fy = cy - floor(cy), fz = cz - floor(cz);
+    const double EPS = 1e-9;
+    if (fx < EPS || fx > 1 - EPS || fy < EPS || fy > 1 - EPS || fz < EPS || fz > 1 - EPS ||
+        fabs(xv - p.xmin) < EPS * LX || fabs(xv - p.xmax) < EPS * LX) {
+      pixel_xyz<P>(p, q, i, xv, yv, zv);
+      cx = (xv + LX / 2) / p.dx; cy = (yv + LY / 2) / p.dy; cz = (zv + LZ / 2 - p.r0) / p.dz;
+    }
     if (!(xv > p.xmin) || !(xv <= p.xmax)) continue;            // owned by another slab
     if (i >= nfor) {                                            // make_spectra.py:99-101
       const size_t o = (size_t)q * p.npix + i;
@@ -251,9 +267,9 @@ __device__ __forceinline__ bool pixel_group_setup(const SkewerParams& p, int q, 
       if (p.flux) store_flux(p, o, i, -1000000.f, 0.f);
       continue;
     }
-    ix[k] = (int)((xv + LX / 2) / p.dx);                        // make_spectra.py:47-49
-    iy[k] = (int)((yv + LY / 2) / p.dy);
-    iz[k] = (int)((zv + LZ / 2 - p.r0) / p.dz);
+    ix[k] = (int)cx;                                            // int() truncates toward zero
+    iy[k] = (int)cy;
+    iz[k] = (int)cz;
     g.ox[k] = (float)((ix[k] + 0.5) * p.dx - LX / 2 - xv);      // cell centre - pixel, make_spectra.py:54-56
     oy[k] = (float)((iy[k] + 0.5) * p.dy - LY / 2 - yv);
     oz[k] = (float)((iz[k] + 0.5) * p.dz - LZ / 2 + p.r0 - zv);
@@ -530,6 +546,7 @@ struct alignas(64) SkewerTmaParams {
   int xw, yw, zl;          // box extent in cells
   int box_elems;           // floats per staged box (xw * yw * zl rounded up to 128 B)
   int* handback;           // [0] = count, [1..] = q * nseg + segment of the segments left to skewers_multi_kernel
+  int* work;               // [0] = entries, [1] = fetch cursor, [2..] = q * nseg + segment (skewers_worklist_kernel)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -590,94 +607,126 @@ __global__ void __launch_bounds__(256) skewers_sentinel_kernel(const __grid_cons
   if (p.flux) store_flux(p, o, i, -1000000.f, 0.f);
 }
 
-// One warp per CTA (NW == 1; the code is written for any NW), each on its own segment of 32*P pixels with its own
-// boxes and mbarriers.  NFG fields are staged and walked together; the boxes of the next stage are in flight while the
-// current ones are walked (two buffers, one mbarrier each).
-template <int P, int NFG, int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) skewers_tma_kernel(const __grid_constant__ SkewerTmaParams t) {
+// Work list of the staged gather: the segments (q * nseg + segment) that hold forest pixels this slab can own, the
+// segments of a sightline next to each other.  work[0] = number of entries, work[1] = fetch cursor of the gather's
+// persistent warps, entries from work[2].  One thread per sightline.
+__global__ void __launch_bounds__(256) skewers_worklist_kernel(const __grid_constant__ SkewerParams p, int seg_pixels,
+                                                               int* __restrict__ work) {
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= p.nqso) return;
+  const int nfor = min(p.npix_forest[q], p.npix);
+  const double X = p.qso[4 * q], R = p.qso[4 * q + 3];
+  // a segment can own pixels here iff the x range of its forest pixels meets (xmin, xmax] (x is monotonic along the
+  // sightline); the margin keeps a segment whose end pixel sits on the slab boundary to the last bit
+  const double margin = 1e-9 * (fabs(p.xmin) + fabs(p.xmax) + 1.0);
+  auto live = [&](int s) {
+    const int ia = s * seg_pixels, ib = min(ia + seg_pixels, nfor) - 1;
+    const double xa = p.rvec[ia] * X / R, xb = p.rvec[ib] * X / R;
+    return fmax(xa, xb) > p.xmin - margin && fmin(xa, xb) <= p.xmax + margin;
+  };
+  const int ns = (nfor + seg_pixels - 1) / seg_pixels;
+  int n = 0;
+  for (int s = 0; s < ns; ++s) n += live(s) ? 1 : 0;
+  if (n == 0) return;
+  int at = 2 + atomicAdd(work, n);
+  for (int s = 0; s < ns; ++s)
+    if (live(s)) work[at++] = q * p.nseg + s;
+}
+
+// Persistent gather: a grid of single-warp CTAs, as many as fit the SMs, each fetching segments of 32*P pixels from the
+// work list until it is empty.  Every warp has its own boxes and mbarriers; NFG fields are staged and walked together,
+// and the boxes of the next stage are in flight while the current ones are walked (two buffers, one mbarrier each).
+template <int P, int NFG, int MINB>
+__global__ void __launch_bounds__(32, MINB) skewers_tma_kernel(const __grid_constant__ SkewerTmaParams t) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const SkewerParams& p = t.p;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long s = (long long)blockIdx.x * NW + warp;
-  if (s >= (long long)p.nqso * p.nseg) return;
-  const int q = (int)(s / p.nseg), seg = (int)(s - (long long)q * p.nseg);
-  if (seg * 32 * P >= p.npix_forest[q]) return;          // beyond the forest: skewers_sentinel_kernel's pixels
+  const int lane = threadIdx.x;
   const uint32_t stage_bytes = (uint32_t)NFG * t.box_elems * 4u;
-  const uint32_t box = smem_u32(smraw) + (uint32_t)warp * 2u * stage_bytes;
-  const uint32_t bar = smem_u32(smraw) + (uint32_t)NW * 2u * stage_bytes + 16u * warp;
+  const uint32_t box = smem_u32(smraw);
+  const uint32_t bar = box + 2u * stage_bytes;
   if (lane == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncwarp();
-  const int i0 = (seg * 32 + lane) * P;
-  PixelGroup<P> g;
-  const bool act = (i0 < p.npix) && pixel_group_setup<P>(p, q, i0, g);
-  if (!__any_sync(0xffffffffu, act)) return;
-  if (!act) pixel_group_idle<P>(g);
-  // the box of the warp: lowest window corner of any live lane; every live lane's 8 x 8 x 8 read must fit into it and
-  // every window must lie inside the slab (TMA fills what is outside the tensor with zeros, which only ever meet the
-  // zero weights of the 8th row / plane / cell)
-  const int BIG = 1 << 30;
-  const int x0 = __reduce_min_sync(0xffffffffu, act ? g.bx : BIG), x1 = __reduce_max_sync(0xffffffffu, act ? g.bx : -BIG);
-  const int y0 = __reduce_min_sync(0xffffffffu, act ? g.by : BIG), y1 = __reduce_max_sync(0xffffffffu, act ? g.by : -BIG);
-  const int z0 = __reduce_min_sync(0xffffffffu, act ? g.bz : BIG), z1 = __reduce_max_sync(0xffffffffu, act ? g.bz : -BIG);
-  // TMA wants the box to start on a 16-byte boundary along the contiguous axis (measured: an innermost coordinate that
-  // is not a multiple of 4 floats raises "illegal instruction", tools/micro/tma_box_test.cu): round the z origin down
-  const int zb = (z0 - DMAX) & ~3;
-  const bool fits = (x1 - x0 + WU <= t.xw) && (y1 - y0 + WU <= t.yw) && (z1 - DMAX + WU - zb <= t.zl);
-  const bool inside = __all_sync(0xffffffffu, !act || group_interior<P>(p, g));
-  if (!fits || !inside) {           // hand the segment back to the global-memory kernel
-    if (lane == 0) t.handback[1 + atomicAdd(t.handback, 1)] = (int)s;
-    return;
-  }
-  const int nxu = __reduce_max_sync(0xffffffffu, g.nxu), nyu = __reduce_max_sync(0xffffffffu, g.nyu);
+  uint32_t parity = 0;              // bit b: phase of buffer b's mbarrier (carried from segment to segment)
+  const int nwork = t.work[0];
+  const int nf = p.rsd ? (p.dla ? 10 : 7) : 1;
   const uint32_t row_bytes = (uint32_t)t.zl * 4u, plane_bytes = (uint32_t)(t.yw * t.zl) * 4u;
   const uint32_t field_bytes = (uint32_t)t.box_elems * 4u;
-  const uint32_t mine = act ? (uint32_t)(((g.bx - x0) * t.yw + (g.by - y0)) * t.zl + (g.bz - DMAX - zb)) * 4u : 0u;
-  const int nf = p.rsd ? (p.dla ? 10 : 7) : 1;
   const uint32_t box_bytes = (uint32_t)(t.xw * t.yw * t.zl) * (uint32_t)sizeof(float);
-  // a stage = the boxes of fields [f0, f0 + NFG) (a last stage that is not full loads its last field again)
-  auto issue = [&](int f0, int buf) {
-    if (lane == 0) {
-      mbar_expect_tx(bar + 8u * buf, NFG * box_bytes);
+#pragma unroll 1
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(t.work + 1, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= nwork) break;
+    const int s = t.work[2 + w];
+    const int q = s / p.nseg, seg = s - q * p.nseg;
+    const int i0 = (seg * 32 + lane) * P;
+    PixelGroup<P> g;
+    const bool act = (i0 < p.npix) && pixel_group_setup<P>(p, q, i0, g);
+    if (!__any_sync(0xffffffffu, act)) continue;
+    if (!act) pixel_group_idle<P>(g);
+    // the box of the warp: lowest window corner of any live lane; every live lane's 8 x 8 x 8 read must fit into it
+    // and every window must lie inside the slab (TMA fills what is outside the tensor with zeros, which only ever meet
+    // the zero weights of the 8th row / plane / cell)
+    const int BIG = 1 << 30;
+    const int x0 = __reduce_min_sync(0xffffffffu, act ? g.bx : BIG), x1 = __reduce_max_sync(0xffffffffu, act ? g.bx : -BIG);
+    const int y0 = __reduce_min_sync(0xffffffffu, act ? g.by : BIG), y1 = __reduce_max_sync(0xffffffffu, act ? g.by : -BIG);
+    const int z0 = __reduce_min_sync(0xffffffffu, act ? g.bz : BIG), z1 = __reduce_max_sync(0xffffffffu, act ? g.bz : -BIG);
+    // TMA wants the box to start on a 16-byte boundary along the contiguous axis (measured: an innermost coordinate
+    // that is not a multiple of 4 floats raises "illegal instruction", tools/micro/tma_box_test.cu): round z down
+    const int zb = (z0 - DMAX) & ~3;
+    const bool fits = (x1 - x0 + WU <= t.xw) && (y1 - y0 + WU <= t.yw) && (z1 - DMAX + WU - zb <= t.zl);
+    const bool inside = __all_sync(0xffffffffu, !act || group_interior<P>(p, g));
+    if (!fits || !inside) {         // hand the segment back to the global-memory kernel
+      if (lane == 0) t.handback[1 + atomicAdd(t.handback, 1)] = s;
+      continue;
+    }
+    const int nxu = __reduce_max_sync(0xffffffffu, g.nxu), nyu = __reduce_max_sync(0xffffffffu, g.nyu);
+    const uint32_t mine = act ? (uint32_t)(((g.bx - x0) * t.yw + (g.by - y0)) * t.zl + (g.bz - DMAX - zb)) * 4u : 0u;
+    // a stage = the boxes of fields [f0, f0 + NFG) (a last stage that is not full loads its last field again)
+    auto issue = [&](int f0, int buf) {
+      if (lane == 0) {
+        mbar_expect_tx(bar + 8u * buf, NFG * box_bytes);
+#pragma unroll
+        for (int f = 0; f < NFG; ++f)
+          tma_load_3d(box + buf * stage_bytes + f * field_bytes, &t.map[min(f0 + f, nf - 1)], zb, y0 - DMAX,
+                      x0 - DMAX - p.ix0, bar + 8u * buf);
+      }
+    };
+    issue(0, 0);                    // in flight under the rest of the set-up
+    const Direction dir = sightline_direction(p, q);
+    PixelResult<P> r;
+    float inv_sw[P], sx[P];
+    sum_x_weights<P>(p, g, sx);
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      r.d0[k] = 0.f; r.eta[k] = 0.f; r.vel[k] = 0.f;
+      inv_sw[k] = ((g.actmask >> k) & 1) ? 1.0f / (sx[k] * g.syz[k]) : 0.f;
+    }
+    // ONE copy of the walk in the instruction stream: the warps of an SM are at different stages, and separate copies
+    // per stage thrashed the instruction cache (profiles/README.md)
+#pragma unroll 1
+    for (int f0 = 0, it = 0; f0 < nf; f0 += NFG, ++it) {
+      const int buf = it & 1;
+      // the other buffer was last read by the walk before this one (every lane passed its __syncwarp): refill it now
+      if (f0 + NFG < nf) issue(f0 + NFG, buf ^ 1);
+      mbar_wait(bar + 8u * buf, (parity >> buf) & 1u);
+      parity ^= 1u << buf;
+      const uint32_t base = box + buf * stage_bytes + mine;
+      float2 acc2[NFG][P];
+      walk_window<P, NFG>(p, g, nxu, nyu,
+                          [&](int f, int a, int b, float2 (&r2)[WU / 2]) {
+                            lds_row8(base + f * field_bytes + a * plane_bytes + b * row_bytes, r2);
+                          },
+                          acc2);
+      __syncwarp();                 // every lane is done with this buffer before the stage after next overwrites it
 #pragma unroll
       for (int f = 0; f < NFG; ++f)
-        tma_load_3d(box + buf * stage_bytes + f * field_bytes, &t.map[min(f0 + f, nf - 1)], zb, y0 - DMAX, x0 - DMAX - p.ix0,
-                    bar + 8u * buf);
+        if (f == 0 || f0 + f < nf) fold_field<P>(f0 + f, field_coefficient(dir, f0 + f), acc2[f], inv_sw, r);
     }
-  };
-  issue(0, 0);                      // in flight under the rest of the set-up
-  const Direction dir = sightline_direction(p, q);
-  PixelResult<P> r;
-  float inv_sw[P], sx[P];
-  sum_x_weights<P>(p, g, sx);
-#pragma unroll
-  for (int k = 0; k < P; ++k) {
-    r.d0[k] = 0.f; r.eta[k] = 0.f; r.vel[k] = 0.f;
-    inv_sw[k] = ((g.actmask >> k) & 1) ? 1.0f / (sx[k] * g.syz[k]) : 0.f;
+    if (act) result_store<P>(p, q, i0, g.actmask, nf, r);
   }
-  uint32_t parity = 0;              // bit b: phase of buffer b's mbarrier
-  // ONE copy of the walk in the instruction stream: the warps of an SM are at different stages, and separate copies per
-  // stage thrashed the instruction cache (profiles/README.md)
-#pragma unroll 1
-  for (int f0 = 0, it = 0; f0 < nf; f0 += NFG, ++it) {
-    const int buf = it & 1;
-    // the other buffer was last read by the walk before this one (every lane passed its __syncwarp): refill it now
-    if (f0 + NFG < nf) issue(f0 + NFG, buf ^ 1);
-    mbar_wait(bar + 8u * buf, (parity >> buf) & 1u);
-    parity ^= 1u << buf;
-    const uint32_t base = box + buf * stage_bytes + mine;
-    float2 acc2[NFG][P];
-    walk_window<P, NFG>(p, g, nxu, nyu,
-                        [&](int f, int a, int b, float2 (&r2)[WU / 2]) {
-                          lds_row8(base + f * field_bytes + a * plane_bytes + b * row_bytes, r2);
-                        },
-                        acc2);
-    __syncwarp();                   // every lane is done with this buffer before the stage after next overwrites it
-#pragma unroll
-    for (int f = 0; f < NFG; ++f)
-      if (f == 0 || f0 + f < nf) fold_field<P>(f0 + f, field_coefficient(dir, f0 + f), acc2[f], inv_sw, r);
-  }
-  if (act) result_store<P>(p, q, i0, g.actmask, nf, r);
 }
 
 // ---------------------------------------------------------------- host side
@@ -752,15 +801,27 @@ static int launch_staged(smk_ctx* ctx, const smk_geom* g, SkewerParams p, cudaSt
   }
   const long long nsegs = (long long)p.nqso * p.nseg;
   if (nsegs > 2147483647LL / 2) { set_error("smk_skewers: too many quasars for one launch"); return SMK_ERR_ARG; }
-  t.handback = (int*)smk_ctx_scratch(ctx, (size_t)(nsegs + 1) * sizeof(int));
+  // scratch: hand-back list [1 + nsegs] and work list [2 + nsegs]
+  t.handback = (int*)smk_ctx_scratch(ctx, (size_t)(2 * nsegs + 4) * sizeof(int));
   if (!t.handback) return SMK_ERR_CUDA;
+  t.work = t.handback + (nsegs + 2);
   SMK_CUDA_OK(cudaMemsetAsync(t.handback, 0, sizeof(int), st));
+  SMK_CUDA_OK(cudaMemsetAsync(t.work, 0, 2 * sizeof(int), st));
   { const int rc = launch_sentinels(p, 32 * P, st); if (rc) return rc; }
-  auto kern = skewers_tma_kernel<P, NFG, 1, MINB>;
+  skewers_worklist_kernel<<<(p.nqso + 255) / 256, 256, 0, st>>>(p, 32 * P, t.work);
+  SMK_CUDA_OK(cudaGetLastError());
+  auto kern = skewers_tma_kernel<P, NFG, MINB>;
   const size_t smem = (size_t)2 * NFG * t.box_elems * sizeof(float) + 16;      // two stages of NFG boxes + two mbarriers
   if (smem > 227 * 1024) return SMK_ERR_UNSUPPORTED;
   SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)nsegs, 32, smem, st>>>(t);
+  int dev = 0, nsm = 0, per_sm = 0;
+  SMK_CUDA_OK(cudaGetDevice(&dev));
+  SMK_CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  SMK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+  if (per_sm < 1) return SMK_ERR_UNSUPPORTED;
+  long long grid = (long long)nsm * per_sm;
+  if (grid > nsegs) grid = nsegs;
+  kern<<<(unsigned)grid, 32, smem, st>>>(t);
   SMK_CUDA_OK(cudaGetLastError());
   g_last.handback = t.handback; g_last.nsegs = nsegs; g_last.xw = t.xw; g_last.yw = t.yw; g_last.zl = t.zl; g_last.st = st;
   // the segments handed back (box edges, oblique segments): fixed grid over the list
