@@ -346,6 +346,8 @@ def run_gpu(args):
     half = chunk_window(nx)[2]
     pipe.set_footprint(ra0, dec0, half, half * ny / nx)
     cells = nx * ny * NZ
+    if world > 1 and args.x_sms is not None:
+        pipe.set_x_sms(args.x_sms)
 
     def barrier():
         if world > 1:
@@ -395,6 +397,23 @@ def run_gpu(args):
     nq_r = [int(v) for v in per_rank(len(pipe.cat["sel"]))]
     t_tot = max(per_rank(t_tot))
     npx = int(sum(pix_r))
+
+    # ---- tuning aid: the box stage with the fused x pass persistent on n CTAs (smk_exchange_set_sms)
+    sweep = {}
+    if world > 1 and args.x_sms_sweep:
+        keep = pipe.x_sms
+        for n in [int(v) for v in args.x_sms_sweep.split(",")]:
+            pipe.set_x_sms(n)
+            pipe.step_boxes(seed=1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(3):
+                pipe.step_boxes(seed=2 + i)
+            e1.record()
+            barrier()
+            sweep[str(n)] = max(per_rank(e0.elapsed_time(e1) / 3))
+        pipe.set_x_sms(keep)
 
     # ---- quasar drawing on the resident boxes (reported beside the step, not part of `value`)
     pipe.draw_qso(seed=1)
@@ -533,7 +552,8 @@ def run_gpu(args):
                 "t_draw_qso_ms": t_qso, "t_draw_qso_kernel_ms": pipe._qso_drawer.last_kernel_ms,
                 "nqso_drawn_rank0": int(nq_drawn),
                 "wall_s": wall, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": pipe.launches_per_step * args.steps,
-                "roofline": roofline, "cpu_baseline": cpu, "parity_selfcheck": selfcheck}
+                "roofline": roofline, "cpu_baseline": cpu, "parity_selfcheck": selfcheck,
+                "x_sms": getattr(pipe, "x_sms", None), "x_sms_sweep_boxes_ms": sweep or None}
         emit(real_stdout, json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -551,6 +571,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-selfcheck", action="store_true", help="skip the sharded-vs-single-GPU parity check (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--x-sms", type=int, default=None, help="N > 1: run the fused-exchange x pass persistent on this many CTAs")
+    ap.add_argument("--x-sms-sweep", default="", help="N > 1: after the timed region, time the box stage for each of these "
+                                                      "comma-separated CTA counts of the persistent x pass (0 = one CTA per tile)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

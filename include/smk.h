@@ -86,6 +86,11 @@ int smk_timing_collect(smk_ctx* ctx, double ms_sum[SMK_NPASSES], int count[SMK_N
  * wtable: device float [nx][ny/R][nz/2+1], directly usable as the `wtable` argument of smk_synth_c2r. */
 int smk_pk_weights(smk_ctx* ctx, const double* breaks, const double* coefs, int nint, float* wtable);
 
+/* ---- float64 1-D FFT for LogNormalP (py/SaclayMocks/powerspectrum.py:145-200: P(k) -> xi(r) -> ln(1 + xi) -> P_ln(k),
+ * two np.fft.fft of 2^20 and 2^19 points): out = unnormalised forward DFT of in, n a power of two; in / out / work are
+ * distinct device arrays of n complex128 (interleaved doubles). */
+int smk_fft1d_f64(smk_ctx* ctx, int n, const double* in, double* out, double* work);
+
 /* ---- 3-D power spectrum estimator on the GPU (the estimator the statistical acceptance
  * tests use, P(k) = <|delta_k|^2> V / N^2): bins |boxk|^2 of this rank's k-slab of a forward transform (smk_fft_r2c of a
  * real box) into `nbins` equal bins of |k| in [kmin, kmax) (h/Mpc), weighting every mode with its Hermitian

@@ -15,7 +15,7 @@ EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy",
            "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
            "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
            "smk_make_boxes_host", "smk_skewers", "smk_skewers_fgpa", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
-           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light", "smk_exchange_set_sms", "smk_skewers_stats", "smk_p1d")
+           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light", "smk_exchange_set_sms", "smk_skewers_stats", "smk_p1d", "smk_fft1d_f64")
 
 
 class SmkError(RuntimeError):
@@ -79,6 +79,7 @@ def lib():
     L.smk_synth_c2r_local_p2p.argtypes = [vp, vp, i, vp, i, d, i]
     L.smk_synth_c2r_finish_p2p.argtypes = [vp, i, vp, vp]
     L.smk_draw_qso.argtypes = [vp, vp, vp, vp, i]
+    L.smk_fft1d_f64.argtypes = [vp, i, vp, vp, vp]
     L.smk_pk_estimate.argtypes = [vp, vp, i, d, d, vp]
     L.smk_timing_enable.argtypes = [vp, i]
     L.smk_timing_collect.argtypes = [vp, C.POINTER(d), C.POINTER(i)]

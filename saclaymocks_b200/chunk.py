@@ -103,10 +103,22 @@ class ChunkPipeline(object):
         xmin, xmax = slab.x_bounds(self.rank, self.nranks, g.LX)
         touch = slab.touching(xyzr, g.R_vec[0], g.R_vec[-1], xmin, xmax)
         sel = np.where(keep & touch)[0]
+        # The staged gather sizes its shared-memory box for the most oblique sightline of a call (include/smk.h:
+        # dir_x_max / dir_y_max).  Sightlines are therefore grouped by the box they need (extent along x and y of a
+        # 128-pixel segment, in steps of two cells) and the gather is called once per group: the near-axis sightlines
+        # of a wide chunk keep the small box and the high occupancy that comes with it.
+        lseg = 127 * g.pixel
+        ex = np.floor(lseg * np.abs(xyzr[sel, 0] / xyzr[sel, 3]) / g.DX).astype(np.int64) // 2
+        ey = np.floor(lseg * np.abs(xyzr[sel, 1] / xyzr[sel, 3]) / g.DY).astype(np.int64) // 2
+        key = ex * 64 + ey
+        sel = sel[np.argsort(key, kind="stable")]
+        key = np.sort(key, kind="stable")
+        starts = np.concatenate(([0], np.where(np.diff(key) != 0)[0] + 1, [len(sel)])) if len(sel) else np.array([0, 0])
+        groups = [(int(a), int(b)) for a, b in zip(starts[:-1], starts[1:]) if b > a]
         ids = np.arange(len(nfor), dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
         self.cat = dict(sel=sel, xyzr=np.ascontiguousarray(xyzr[sel]), nfor=np.ascontiguousarray(nfor[sel]),
                         ids=ids[sel], z=np.asarray(z)[sel], xmin=xmin, xmax=xmax, n_total=len(nfor),
-                        kept=np.where(keep)[0], xyzr_kept=np.ascontiguousarray(xyzr[keep]))
+                        kept=np.where(keep)[0], xyzr_kept=np.ascontiguousarray(xyzr[keep]), groups=groups)
         nq, npix = len(sel), g.npixeltot
         self.cat["xyzr_d"] = torch.as_tensor(self.cat["xyzr"], device=self.device)
         self.cat["nfor_d"] = torch.as_tensor(self.cat["nfor"], device=self.device)
@@ -276,29 +288,34 @@ class ChunkPipeline(object):
         fl = (C.c_void_p * 10)()
         for i, k in enumerate(sp.FIELDS):
             fl[i] = self.fields[k].data_ptr()
-        cg = self.geom.c_geom(c["xyzr"])
         ix0 = self.rank * self.bs.nxl - self.hlo
         nxs = self.bs.nxl + self.hlo + self.hhi
         L = self.bs.lib
         # small-scale field first, then the gather with the FGPA in its epilogue (delta_l / eta_par are not read back)
         ds = self.fgpa.small_scales(c["nf_merge"], noise=noise, seed=seed, prepared=c["prep"])
-        args = (self.bs.h, C.byref(cg), fl, ix0, nxs, C.c_double(c["xmin"]), C.c_double(c["xmax"]), int(self.rsd),
-                int(self.dla), nq, _ptr(c["xyzr_d"]), _ptr(c["nfor_d"]), _ptr(self.eng.rvec), npix, _ptr(dl), _ptr(ep),
-                _ptr(vp))
-        timed = getattr(self, "gather_events", None)        # bench.py: CUDA events around the gather kernel
+        timed = getattr(self, "gather_events", None)        # bench.py: CUDA events around the gather kernels
         if timed is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        if os.environ.get("SMK_FUSED_FGPA", "1") != "0":
-            _lib.check(L.smk_skewers_fgpa(*args, _ptr(ds), _ptr(self.fgpa.G), _ptr(self.fgpa.a), _ptr(self.fgpa.b),
-                                          _ptr(self.fgpa.c), _ptr(F)))
-            if timed is not None:
-                e1.record()
-                timed.append((e0, e1))
-        else:
-            _lib.check(L.smk_skewers(*args))
+        fused = os.environ.get("SMK_FUSED_FGPA", "1") != "0"
+        self.gather_stats = []
+        for a, b in c["groups"]:                            # one call per box class (set_catalogue), rows [a, b)
+            cg = self.geom.c_geom(c["xyzr"][a:b])
+            row = lambda t: C.c_void_p(t.data_ptr() + a * t.stride(0) * t.element_size())
+            args = (self.bs.h, C.byref(cg), fl, ix0, nxs, C.c_double(c["xmin"]), C.c_double(c["xmax"]), int(self.rsd),
+                    int(self.dla), b - a, row(c["xyzr_d"]), row(c["nfor_d"]), _ptr(self.eng.rvec), npix, row(dl), row(ep),
+                    row(vp))
+            if fused:
+                _lib.check(L.smk_skewers_fgpa(*args, row(ds), _ptr(self.fgpa.G), _ptr(self.fgpa.a), _ptr(self.fgpa.b),
+                                              _ptr(self.fgpa.c), row(F)))
+            else:
+                _lib.check(L.smk_skewers(*args))
+        if not fused:
             _lib.check(L.smk_fgpa(self.bs.h, nq, npix, _ptr(dl), _ptr(ds), _ptr(ep), _ptr(self.fgpa.G),
                                   _ptr(self.fgpa.a), _ptr(self.fgpa.b), _ptr(self.fgpa.c), _ptr(F)))
+        if timed is not None:
+            e1.record()
+            timed.append((e0, e1))
         self.delta_s = ds
         return self.out
 
@@ -321,6 +338,8 @@ class ChunkPipeline(object):
             res["delta_s"] = self.delta_s
             return res
         plan = slab.row_gather_plan(c["xyzr_kept"], g.R_vec[0], g.R_vec[-1], self.nranks, g.LX, self.rank)
+        # the plan counts local rows in ascending catalogue order; the local rows are grouped by box class (set_catalogue)
+        plan["send_rows"] = np.argsort(c["sel"], kind="stable")[plan["send_rows"]]
         res = {"index": c["kept"][plan["home_qso"]]}
         for k, t in zip(names + ("delta_s",), self.out + (self.delta_s,)):
             res[k] = slab.exchange_rows(t, plan, group=self.group)

@@ -86,3 +86,47 @@ int launch_pk_weights(const PkParams& p, cudaStream_t st) {
 }
 
 }  // namespace smk
+
+// ---- float64 1-D complex FFT on the GPU for the P(k) <-> xi(r) pair of LogNormalP (py/SaclayMocks/powerspectrum.py:
+// 145-200: two np.fft.fft of 2^20 and 2^19 points).  Stockham autosort radix 2: log2(n) passes over global memory,
+// ping-ponging between two buffers, twiddles from sincospi in float64 (error ~1e-16 like pocketfft's).  The arrays
+// are a few MB and the passes a few microseconds each: nothing here needs shared memory.
+namespace smk {
+
+// one pass: sub-transform length len (n / stride), stride = number of interleaved sequences
+__global__ void __launch_bounds__(256) fft1d_pass_kernel(const double2* __restrict__ x, double2* __restrict__ y, int len,
+                                                         int stride, int half_n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= half_n) return;
+  const int m = len >> 1;
+  const int p = t / stride, q = t - p * stride;            // butterfly p of the current length, sequence q
+  double s, c;
+  sincospi(-2.0 * (double)p / (double)len, &s, &c);        // w = exp(-2 pi i p / len)
+  const double2 a = x[q + stride * p], b = x[q + stride * (p + m)];
+  const double2 d = make_double2(a.x - b.x, a.y - b.y);
+  y[q + stride * (2 * p)] = make_double2(a.x + b.x, a.y + b.y);
+  y[q + stride * (2 * p + 1)] = make_double2(d.x * c - d.y * s, d.x * s + d.y * c);
+}
+
+}  // namespace smk
+
+extern "C" int smk_fft1d_f64(smk_ctx* ctx, int n, const double* in, double* out, double* work) {
+  using namespace smk;
+  if (!in || !out || !work || n < 2 || (n & (n - 1))) { set_error("smk_fft1d_f64: n must be a power of two >= 2"); return SMK_ERR_ARG; }
+  if (in == out || in == work || out == work) { set_error("smk_fft1d_f64: in, out and work must be distinct"); return SMK_ERR_ARG; }
+  cudaStream_t st = smk_ctx_stream(ctx);
+  int passes = 0;
+  for (int v = n; v > 1; v >>= 1) ++passes;
+  // the last pass must land in `out`: the first pass writes to out when the number of passes is odd, else to work
+  const double2* src = reinterpret_cast<const double2*>(in);
+  double2* a = reinterpret_cast<double2*>((passes & 1) ? out : work);
+  double2* b = reinterpret_cast<double2*>((passes & 1) ? work : out);
+  const int half = n / 2;
+  for (int len = n, stride = 1; len > 1; len >>= 1, stride <<= 1) {
+    fft1d_pass_kernel<<<(half + 255) / 256, 256, 0, st>>>(src, a, len, stride, half);
+    SMK_CUDA_OK(cudaGetLastError());
+    src = a;
+    double2* tmp = a; a = b; b = tmp;
+  }
+  return SMK_OK;
+}

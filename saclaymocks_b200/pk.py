@@ -26,7 +26,7 @@ def _input_pk(G_times_bias=1.0):
     return k, P
 
 
-def _hankel(k, pk, n, forward_scale):
+def _hankel(k, pk, n, forward_scale, fft=None):
     """One direction of the P(k) <-> xi(r) pair on a uniform grid of n points up to max(k)
     (powerspectrum.py:151-176): xi(r) = -Im FFT[k P(k)] / (2 pi^2 r) * dk-normalisation."""
     spl = InterpolatedUnivariateSpline(k, pk)
@@ -35,17 +35,36 @@ def _hankel(k, pk, n, forward_scale):
     r = 2. * np.pi * np.arange(n) / kmax
     integrand = kin * spl(kin)
     r[0] = 1e-10
-    xi = -np.imag(np.fft.fft(integrand) / n) / r / 2. / np.pi ** 2 * kmax
+    xi = -np.imag((fft or np.fft.fft)(integrand) / n) / r / 2. / np.pi ** 2 * kmax
     r[0] = 0
     xi[0] = InterpolatedUnivariateSpline(k, pk * k * k).integral(0, kmax) / 2 / np.pi ** 2
     return r[:n // 2], xi[:n // 2] * forward_scale
 
 
-def lognormal_pk(k, P, nk=1024 * 1024):
-    """P(k) -> xi(r) -> ln(1 + xi) -> P_ln(k)   (powerspectrum.py:194-200)."""
-    r, xi = _hankel(k, P, nk, 1.0)
-    kln, Pln = _hankel(r, np.log(1 + xi), nk // 2, (2 * np.pi) ** 3)
+def lognormal_pk(k, P, nk=1024 * 1024, fft=None):
+    """P(k) -> xi(r) -> ln(1 + xi) -> P_ln(k)   (powerspectrum.py:194-200).  fft: the transform to use (default
+    np.fft.fft; gpu_fft() runs the two 2^20 / 2^19-point float64 transforms on the GPU, smk_fft1d_f64)."""
+    r, xi = _hankel(k, P, nk, 1.0, fft)
+    kln, Pln = _hankel(r, np.log(1 + xi), nk // 2, (2 * np.pi) ** 3, fft)
     return kln, np.maximum(Pln, 0)
+
+
+def gpu_fft(device=None):
+    """np.fft.fft replacement for 1-D float64 / complex128 arrays of power-of-two length on the GPU (smk_fft1d_f64)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    ctx = _lib.StreamCtx(dev)
+
+    def fft(a):
+        x = torch.as_tensor(np.ascontiguousarray(a, dtype=np.complex128), device=dev)
+        n = x.numel()
+        out, work = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(ctx.lib.smk_fft1d_f64(ctx.handle(), n, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                         C.c_void_p(work.data_ptr())))
+        return out.cpu().numpy()
+    return fft
 
 
 def spline(name):

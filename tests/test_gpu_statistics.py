@@ -217,3 +217,22 @@ def test_p1d_of_flux_against_cpu_oracle_on_the_same_boxes(cuda):
     assert np.max(np.abs(p_gpu[sel] / p_cpu[sel] - 1)) < 1e-4
     assert np.all(err[sel] / p_gpu[sel] > 5e-2)                      # the statistical error is orders of magnitude larger
     bs.close()
+
+
+def test_gpu_lognormal_pk_matches_host(cuda):
+    """GPU LogNormalP (powerspectrum.py:194-200 with the two 1-D float64 transforms on the GPU, smk_fft1d_f64) against
+    the host version (numpy / pocketfft): the transform itself to 1e-12 of the largest mode, P_ln(k) to 1e-9 relative
+    wherever it matters for the weight tables."""
+    from saclaymocks_b200 import pk
+    fft = pk.gpu_fft(cuda)
+    rng = np.random.default_rng(2)
+    for n in (2, 8, 1 << 10, 1 << 19, 1 << 20):
+        a = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        ref = np.fft.fft(a)
+        assert np.max(np.abs(fft(a) - ref)) < 1e-12 * max(1.0, np.abs(ref).max()), n
+    k, P = pk._input_pk(pk.fgrowth(2.75, pk.constant.omega_M_0) * pk.bias_qso(2.75))
+    kh, Ph = pk.lognormal_pk(k, P)
+    kg, Pg = pk.lognormal_pk(k, P, fft=fft)
+    assert np.array_equal(kh, kg)
+    sel = Ph > 1e-6 * Ph.max()
+    assert np.max(np.abs(Pg[sel] / Ph[sel] - 1)) < 1e-9
