@@ -54,6 +54,16 @@ enum smk_product {
 const char* smk_last_error(void);
 int smk_version(void);
 
+/* Library options (process-wide).  The library reads no environment variable; these are the switches the parity tests
+ * use and the alternatives that lost their measurements:
+ *   "skewers_kernel"  0 = staged (TMA) gather with the global-memory kernel for what it hands back [default],
+ *                     1 = global-memory gather for everything, 2 = one pixel per thread (no register blocking);
+ *   "qso_exact"       1 = smk_draw_qso uses the reference-arithmetic kernel with Philox draws as well;
+ *   "yz_group", "yz_streams", "yz_persist", "yz_discard"  y/z passes chained through L2 in groups of yz_group planes
+ *                     (0 = off, default), read by smk_ctx_create.
+ * Returns SMK_ERR_ARG for an unknown name. */
+int smk_set_option(const char* name, int value);
+
 /* ---- context / plan.  Replaces the pyfftw plan + wisdom handling of make_boxes.py:192-203.
  * dcell = cell size in Mpc/h (make_boxes.py -pixel).  stream = cudaStream_t (NULL = default stream).
  * rank/nranks describe the slab decomposition; nranks > 1 requires nx % nranks == 0 and ny % nranks == 0. */

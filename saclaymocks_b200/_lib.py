@@ -15,7 +15,7 @@ EXPORTS = ("smk_last_error", "smk_version", "smk_ctx_create", "smk_ctx_destroy",
            "smk_box_elems", "smk_workspace_bytes", "smk_sync", "smk_noise_philox", "smk_fft_r2c", "smk_fft_r2c_local",
            "smk_fft_r2c_finish", "smk_synth_c2r", "smk_synth_c2r_local", "smk_synth_c2r_finish",
            "smk_make_boxes_host", "smk_skewers", "smk_skewers_fgpa", "smk_smallscale", "smk_fgpa", "smk_timing_enable", "smk_timing_collect", "smk_pk_weights", "smk_exchange_create", "smk_exchange_handle",
-           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light", "smk_exchange_set_sms", "smk_skewers_stats", "smk_p1d", "smk_fft1d_f64")
+           "smk_exchange_connect", "smk_exchange_ptr", "smk_synth_c2r_local_p2p", "smk_synth_c2r_finish_p2p", "smk_set_stream", "smk_draw_qso", "smk_pk_estimate", "smk_ctx_create_light", "smk_exchange_set_sms", "smk_skewers_stats", "smk_p1d", "smk_fft1d_f64", "smk_set_option")
 
 
 class SmkError(RuntimeError):
@@ -44,6 +44,7 @@ def lib():
     L.smk_last_error.restype = C.c_char_p
     L.smk_version.restype = i
     L.smk_ctx_create.argtypes = [C.POINTER(vp), i, i, i, d, i, i, vp]
+    L.smk_set_option.argtypes = [C.c_char_p, i]
     L.smk_ctx_create_light.argtypes = [C.POINTER(vp), vp]
     L.smk_ctx_destroy.argtypes = [vp]
     L.smk_boxk_pitch.argtypes = [vp]
@@ -126,6 +127,21 @@ def skewers_stats(ctx=None):
     seg, back, box = C.c_longlong(), C.c_longlong(), (C.c_int * 3)()
     check(lib().smk_skewers_stats(ctx, C.byref(seg), C.byref(back), box))
     return int(seg.value), int(back.value), tuple(box)
+
+
+class option(object):
+    """with _lib.option("skewers_kernel", 1): ...  -- a library option (smk_set_option) for the duration of a block."""
+    DEFAULTS = {"skewers_kernel": 0, "qso_exact": 0, "yz_group": 0, "yz_streams": 2, "yz_persist": 0, "yz_discard": 1}
+
+    def __init__(self, name, value):
+        self.name, self.value = name, int(value)
+
+    def __enter__(self):
+        check(lib().smk_set_option(self.name.encode(), self.value))
+        return self
+
+    def __exit__(self, *a):
+        check(lib().smk_set_option(self.name.encode(), self.DEFAULTS[self.name]))
 
 
 def check(rc):

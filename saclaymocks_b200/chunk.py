@@ -78,7 +78,11 @@ class ChunkPipeline(object):
         # x pass on a high-priority stream: its CTAs are placed first; with set_x_sms(n > 0) it runs persistent on n CTAs
         # and the y / z passes of the other stream fill the remaining SMs (SMK_X_SMS = initial value, default 0 = off)
         self._xstream = torch.cuda.Stream(device=self.device, priority=-1)
-        self.set_x_sms(int(os.environ.get("SMK_X_SMS", "0") or 0))
+        # measured on 8 x B200 at the nominal size (bench.py --x-sms-sweep, profiles/README.md): boxes 184 ms with one CTA
+        # per tile, 318 / 226 / 179 / 167 ms persistent on 32 / 48 / 64 / 96 CTAs -- the x pass is NVLink-bound there;
+        # at 2 ranks it is HBM-bound and capping it loses
+        default = 96 if self.nranks >= 8 else 0
+        self.set_x_sms(int(os.environ.get("SMK_X_SMS", str(default)) or 0))
         dist.barrier(group=self.group)
 
     def set_x_sms(self, n):
@@ -127,12 +131,18 @@ class ChunkPipeline(object):
         # rows are written only at the pixels this slab owns (smk_skewers: xmin < X <= xmax); everything else keeps this
         # NaN, which is what merging the slabs' pieces selects on (gather_rows; bin/make_spectra.py relies on the same mask)
         self.out = tuple(torch.full((nq, npix), float("nan"), dtype=torch.float32, device=self.device) for _ in range(4))
-        # pixels this rank owns: xmin < X <= xmax and inside the forest (for the pixel-rate metric)
-        own = 0
-        for i0 in range(0, nq, 4096):
-            X = self.cat["xyzr"][i0:i0 + 4096, 0:1] * g.R_vec[None, :] / self.cat["xyzr"][i0:i0 + 4096, 3:4]
-            inside = (X > xmin) & (X <= xmax) & (np.arange(npix)[None, :] < self.cat["nfor"][i0:i0 + 4096, None])
-            own += int(inside.sum())
+        self.delta_s = torch.zeros((nq, npix), dtype=torch.float32, device=self.device)
+        # pixels this rank owns: xmin < X <= xmax and inside the forest (for the pixel-rate metric).  X = x_q r / R_q is
+        # monotonic along the sightline, so the owned pixels of a sightline are one interval of the pixel grid
+        cx, cR, cn = self.cat["xyzr"][:, 0], self.cat["xyzr"][:, 3], self.cat["nfor"].astype(np.int64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r_min, r_max = xmin * cR / cx, xmax * cR / cx
+        lo = np.where(cx > 0, np.searchsorted(g.R_vec, r_min, side="right"), np.searchsorted(g.R_vec, r_max, side="left"))
+        hi = np.where(cx > 0, np.searchsorted(g.R_vec, r_max, side="right"), np.searchsorted(g.R_vec, r_min, side="left"))
+        zero = cx == 0
+        lo = np.where(zero, 0, lo)
+        hi = np.where(zero, npix if xmin < 0 <= xmax else 0, hi)
+        own = int(np.clip(np.minimum(hi, cn) - lo, 0, None).sum())
         self.cat["own_pixels"] = own
 
     def forest_pixels_total(self):
@@ -368,7 +378,7 @@ class ChunkPipeline(object):
             self._qso_drawer = qso.QsoDrawer(bs)
         return self._qso_drawer.draw(self._qso_setup, [self.interior("boxln_%d" % k) for k in (1, 2, 3)],
                                      [self.interior(k) for k in ("vx", "vy", "vz")] if self.rsd else None,
-                                     ix0=self.rank * bs.nxl, uniforms=uniforms, seed=seed, chunk=fp["chunk"])
+                                     ix0=self.rank * bs.nxl, uniforms=uniforms, seed=seed, chunk=fp["chunk"], pmf=False)
 
     # ------------------------------------------------------------------ one chunk of the footprint, device resident
     def run_chunk(self, chunk=1, seed=0, cells=None, stripe_footprint=False):
@@ -380,19 +390,33 @@ class ChunkPipeline(object):
         as a dict of numpy columns, (delta_l, eta_par, vpar, flux) device rows of the quasars whose sightline touches
         this rank's slab -- row i belongs to catalogue entry self.cat["sel"][i])."""
         from . import chunks
+        import time
         ra0, dra, dec0, ddec = chunks.chunk_window(cells if cells is not None else self.bs.NX, chunk, stripe_footprint)
         self.set_footprint(ra0, dec0, dra, ddec, chunk=int(chunk))
+        tm, t0 = {}, time.time()
+
+        def lap(name):                      # wall time of each phase (device work included: synchronised)
+            nonlocal t0
+            torch.cuda.synchronize(self.device)
+            tm[name] = time.time() - t0
+            t0 = time.time()
         self.step_boxes(seed)
+        lap("boxes")
         mine = self.draw_qso(seed)
+        lap("draw_qso")
         cols = ("RA", "DEC", "Z_QSO_NO_RSD", "Z_QSO_RSD", "HDU", "THING_ID")
         parts = [{c: mine[c] for c in cols}]
         if self.nranks > 1:                      # every rank needs the quasars of all slabs: a sightline crosses slabs
             parts = [None] * self.nranks
             torch.distributed.all_gather_object(parts, {c: mine[c] for c in cols}, group=self.group)
         cat = {c: np.concatenate([p[c] for p in parts]) for c in cols}
+        lap("catalogue_allgather")
         z = cat["Z_QSO_RSD"] if self.rsd else cat["Z_QSO_NO_RSD"]              # make_spectra.py:417-420
         self.set_catalogue(cat["RA"], cat["DEC"], z, ra0, dec0, ids=cat["THING_ID"])
+        lap("sightline_setup_host")
         self.step_skewers(seed)
+        lap("skewers")
+        self.last_chunk_timings = tm
         return cat, self.out
 
     # ------------------------------------------------------------------ end-to-end through host buffers

@@ -103,18 +103,31 @@ static int make_ktable(int n, bool rfft, double dcell, float** dptr, size_t* byt
 // overwritten group after group and therefore stays resident in the 126 MB L2: the y pass's writes and the z pass's
 // reads never reach HBM, and a 3-D transform moves 16 B per real cell instead of 24.  Groups are issued round robin on
 // a few internal streams (each with its own slot) so that the tail of one group's kernels overlaps the next group's.
-// SMK_YZ_GROUP = planes per group (0 disables), SMK_YZ_STREAMS = 1..4, SMK_YZ_PERSIST = 1 pins the slots in L2 with an
-// access-policy window.
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
+// Options yz_group = planes per group (0 disables: the default, the chained form measured slower than the plain passes),
+// yz_streams = 1..4, yz_persist = 1 pins the slots in L2 with an access-policy window.
+// ---- library options (smk_set_option): switches for parity tests and for the alternatives that lost their sweeps.
+// Process-wide, read when a context is created (yz_*) or a call is made (skewers_kernel, qso_exact); no environment
+// variable is read anywhere in the library.
+#include <map>
+#include <mutex>
+static std::mutex g_opt_mutex;
+static std::map<std::string, int>& options() {
+  static std::map<std::string, int> o = {{"skewers_kernel", 0}, {"qso_exact", 0}, {"yz_group", SMK_YZ_GROUP_DEFAULT},
+                                         {"yz_streams", SMK_YZ_STREAMS_DEFAULT}, {"yz_persist", 0}, {"yz_discard", 1}};
+  return o;
 }
+int smk_option(const char* name) {
+  std::lock_guard<std::mutex> lock(g_opt_mutex);
+  auto it = options().find(name);
+  return it == options().end() ? 0 : it->second;
+}
+static int env_int(const char* name, int) { return smk_option(name); }
 
 static int chain_setup(smk_ctx* c) {
-  int g = env_int("SMK_YZ_GROUP", SMK_YZ_GROUP_DEFAULT);
+  int g = env_int("yz_group", 0);
   if (g <= 0) return SMK_OK;
   if (g > c->nxl) g = c->nxl;
-  int ns = env_int("SMK_YZ_STREAMS", SMK_YZ_STREAMS_DEFAULT);
+  int ns = env_int("yz_streams", 0);
   ns = ns < 1 ? 1 : (ns > 4 ? 4 : ns);
   const size_t slot = (size_t)g * c->ny * c->pitch * sizeof(float2);
   SMK_CUDA_OK(cudaMalloc(&c->yz_scratch, slot * ns));
@@ -124,7 +137,7 @@ static int chain_setup(smk_ctx* c) {
     SMK_CUDA_OK(cudaStreamCreateWithFlags(&c->yz_stream[s], cudaStreamNonBlocking));
     SMK_CUDA_OK(cudaEventCreateWithFlags(&c->yz_join[s], cudaEventDisableTiming));
   }
-  if (env_int("SMK_YZ_PERSIST", 0)) {
+  if (env_int("yz_persist", 0)) {
     int dev = 0, maxwin = 0, maxpersist = 0;
     SMK_CUDA_OK(cudaGetDevice(&dev));
     SMK_CUDA_OK(cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, dev));
@@ -144,7 +157,7 @@ static int chain_setup(smk_ctx* c) {
   }
   c->yz_group = g;
   c->yz_streams = ns;
-  c->yz_discard = env_int("SMK_YZ_DISCARD", 1) != 0;
+  c->yz_discard = env_int("yz_discard", 1) != 0;
   return SMK_OK;
 }
 
@@ -237,6 +250,14 @@ static int ctx_allocate(smk_ctx* c) {
 extern "C" {
 
 const char* smk_last_error(void) { return g_err.c_str(); }
+
+int smk_set_option(const char* name, int value) {
+  std::lock_guard<std::mutex> lock(g_opt_mutex);
+  auto it = name ? options().find(name) : options().end();
+  if (it == options().end()) { set_error(std::string("smk_set_option: unknown option ") + (name ? name : "(null)")); return SMK_ERR_ARG; }
+  it->second = value;
+  return SMK_OK;
+}
 int smk_version(void) { return 100; }
 
 int smk_ctx_create(smk_ctx** out, int nx, int ny, int nz, double dcell, int rank, int nranks, void* stream) {

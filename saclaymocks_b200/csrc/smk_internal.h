@@ -103,3 +103,5 @@ cudaStream_t smk_ctx_stream(const smk_ctx* ctx);
 void* smk_ctx_scratch(smk_ctx* ctx, size_t bytes);
 // device twiddle table W_nfft[k] = exp(-2 pi i k / nfft) of the 1-D transforms, cached per (device, nfft)
 int smk_tw1d(int nfft, const float2** out);
+// value of a library option (smk_set_option; 0 for an unknown name)
+int smk_option(const char* name);

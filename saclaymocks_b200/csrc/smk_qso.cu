@@ -306,8 +306,8 @@ extern "C" int smk_draw_qso(smk_ctx* ctx, const smk_qso_params* p, int* counters
   if (blocks > 148 * 32) blocks = 148 * 32;
   cudaStream_t st = smk_ctx_stream(ctx);
   const bool aligned = (((uintptr_t)p->boxln[0] | (uintptr_t)p->boxln[1] | (uintptr_t)p->boxln[2]) & 15) == 0;
-  const char* env = getenv("SMK_QSO_EXACT");          // force the reference-arithmetic kernel in Philox mode too
-  if (!p->u1 && p->nz % 4 == 0 && aligned && !(env && env[0] == '1')) {
+  const bool exact = smk_option("qso_exact") != 0;    // parity tests: the reference-arithmetic kernel in Philox mode too
+  if (!p->u1 && p->nz % 4 == 0 && aligned && !exact) {
     char* scratch = (char*)smk_ctx_scratch(ctx, sizeof(QsoLut) + sizeof(smk_qso_params));
     if (!scratch) return SMK_ERR_CUDA;
     QsoLut* lut = (QsoLut*)scratch;

@@ -22,10 +22,6 @@
 
 #include "smk_internal.h"
 
-#ifndef SMK_SKEW_VARIANT_DEFAULT
-#define SMK_SKEW_VARIANT_DEFAULT 41   // 4 pixels per thread, 1 field per stage, 12 warps per SM
-#endif
-
 namespace smk {
 
 struct SkewerParams {
@@ -845,15 +841,9 @@ int launch_skewers(smk_ctx* ctx, const smk_geom* g, SkewerParams& p, int dmax, d
   if (blocked_ok(4)) {
     if (fused) *fused = true;
     if (staged && ctx) {
-      // experiment switch (pixels per thread x fields per stage); the default is the measured best (profiles/README.md)
-      const char* e = getenv("SMK_SKEW_VARIANT");
-      const int variant = e ? atoi(e) : SMK_SKEW_VARIANT_DEFAULT;
-      int rc = SMK_ERR_UNSUPPORTED;
-      if (variant == 4116) rc = launch_staged<4, 1, 16>(ctx, g, p, st);          // 128 registers, 16 warps
-      else if (variant == 418) rc = launch_staged<4, 1, 8>(ctx, g, p, st);       // 255 registers, 8 warps
-      else if (variant == 428) rc = launch_staged<4, 2, 8>(ctx, g, p, st);
-      else if (variant == 42) rc = launch_staged<4, 2, 12>(ctx, g, p, st);
-      else rc = launch_staged<4, 1, 12>(ctx, g, p, st);                          // 41: 168 registers, 12 warps
+      // 4 pixels per thread, one field per stage, up to 12 single-warp CTAs per SM: the measured best of the variants
+      // tried on B200 (two fields per stage; 8 / 12 / 16 warps per SM; 6 and 8 pixels per thread: profiles/README.md)
+      const int rc = launch_staged<4, 1, 12>(ctx, g, p, st);
       if (rc != SMK_ERR_UNSUPPORTED) return rc;
     }
     p.nseg = (p.npix + 32 * 4 - 1) / (32 * 4);
@@ -911,13 +901,12 @@ static int skewers_impl(smk_ctx* ctx, const smk_geom* g, const float* const fiel
   p.delta_l = delta_l; p.eta_par = eta_par; p.vpar = vpar;
   p.delta_s = delta_s; p.fg_G = growthf; p.fg_a = fa; p.fg_b = fb; p.fg_c = fc; p.flux = flux;
   // largest step between consecutive pixels of the grid (uniform 0.2 Mpc/h in the reference); decides whether the
-  // register-blocked kernels may be used.  Parity-test switches: SMK_SKEWERS_SIMPLE=1 forces the one-pixel-per-thread
-  // kernel, SMK_SKEWERS_STAGED=0 the global-memory walk for every segment.
+  // register-blocked kernels may be used.  Parity-test switch (smk_set_option "skewers_kernel"): 1 = the global-memory
+  // walk for every segment, 2 = the one-pixel-per-thread kernel.
   double step = g->pixel_step;
-  const char* env = getenv("SMK_SKEWERS_SIMPLE");
-  if (env && env[0] == '1') step = 0.0;
-  env = getenv("SMK_SKEWERS_STAGED");
-  const bool staged = !(env && env[0] == '0');
+  const int which = smk_option("skewers_kernel");
+  if (which == 2) step = 0.0;
+  const bool staged = which == 0;
   bool fused = false;
   int rc = launch_skewers(ctx, g, p, g->dmax, step, staged, smk_ctx_stream(ctx), &fused);
   if (rc != SMK_OK || !flux || fused) return rc;

@@ -204,9 +204,11 @@ class QsoDrawer(object):
         st._prepared = (p, keep, self.device)
         return p, keep
 
-    def draw(self, setup, boxln, velo=None, ix0=0, uniforms=None, seed=0, capacity=None, chunk=0, rs=None):
+    def draw(self, setup, boxln, velo=None, ix0=0, uniforms=None, seed=0, capacity=None, chunk=0, rs=None, pmf=True):
         """boxln: three device float32 [NXs, NY, NZ] tensors (boxln_1..3 of this slab, NOT exponentiated);
-        velo: (vx, vy, vz) or None (rsd off).  Returns the QSO-<i>-<N>.fits columns as a dict of numpy arrays."""
+        velo: (vx, vy, vz) or None (rsd off).  Returns the QSO-<i>-<N>.fits columns as a dict of numpy arrays.
+        pmf=False leaves out the PLATE-MJD-FIBERID strings (a Python loop over the quasars: 10 ms per 15 000 of them,
+        more than the kernel); write_qso_file() builds them when they are missing."""
         st = setup
         dev = self.device
         for t in tuple(boxln) + tuple(velo or ()):
@@ -253,12 +255,19 @@ class QsoDrawer(object):
         rs = rs if rs is not None else np.random.RandomState(int(seed) % (2 ** 32))
         mjd = rs.randint(51608, high=57521, size=n)
         fiberid = rs.randint(1, high=1001, size=n)
-        pmf = np.array(["%d-%d-%d" % (t, m, f) for t, m, f in zip(thing_id, mjd, fiberid)], dtype="S21")
-        return {"Z_QSO_NO_RSD": np.float32(rec[:, 1]), "Z_QSO_RSD": np.float32(rec[:, 2]), "RA": np.float32(rec[:, 3]),
-                "DEC": np.float32(rec[:, 4]), "HDU": np.int32(np.ones(n) * st.i_slice), "THING_ID": thing_id,
-                "PLATE": thing_id, "MJD": np.int32(mjd), "FIBERID": np.int32(fiberid), "PMF": pmf,
-                "XX": np.float32(rec[:, 5]), "YY": np.float32(rec[:, 6]), "ZZ": np.float32(rec[:, 7]),
-                "cells": cells, "nn_cond1": nn, "f64": rec}
+        cat = {"Z_QSO_NO_RSD": np.float32(rec[:, 1]), "Z_QSO_RSD": np.float32(rec[:, 2]), "RA": np.float32(rec[:, 3]),
+               "DEC": np.float32(rec[:, 4]), "HDU": np.int32(np.ones(n) * st.i_slice), "THING_ID": thing_id,
+               "PLATE": thing_id, "MJD": np.int32(mjd), "FIBERID": np.int32(fiberid),
+               "XX": np.float32(rec[:, 5]), "YY": np.float32(rec[:, 6]), "ZZ": np.float32(rec[:, 7]),
+               "cells": cells, "nn_cond1": nn, "f64": rec}
+        if pmf:
+            cat["PMF"] = pmf_strings(cat)
+        return cat
+
+
+def pmf_strings(cat):
+    """PLATE-MJD-FIBERID of draw_qso.py:500-503 as fixed-width byte strings."""
+    return np.array(["%d-%d-%d" % (t, m, f) for t, m, f in zip(cat["PLATE"], cat["MJD"], cat["FIBERID"])], dtype="S21")
 
 
 def box_sigma(box):
@@ -275,6 +284,8 @@ COLUMNS = ("Z_QSO_NO_RSD", "Z_QSO_RSD", "RA", "DEC", "HDU", "THING_ID", "PLATE",
 def write_qso_file(path, cat, seed, ra0, dec0):
     """QSO-<i>-<N>.fits in the layout of draw_qso.py:523-563."""
     from . import fitsio_lite as fitsio
+    if "PMF" not in cat:
+        cat = dict(cat, PMF=pmf_strings(cat))
     f = fitsio.FITS(path, "rw", clobber=True)
     f.write([cat[c] for c in COLUMNS], names=list(COLUMNS),
             header=[{"name": "seed", "value": int(seed), "comment": "seed used to generate randoms"},

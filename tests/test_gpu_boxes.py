@@ -48,15 +48,15 @@ def test_boxes_match_oracle(cuda, shape, dcell):
 
 
 @pytest.mark.parametrize("group,streams", [(1, 1), (3, 2), (8, 3), (64, 2)])
-def test_boxes_chained_yz_match_oracle(cuda, monkeypatch, group, streams):
+def test_boxes_chained_yz_match_oracle(cuda, group, streams):
     """y<->z passes chained through an L2-resident scratch slot (plane groups on internal streams, ragged last
     group, L2 discard of the dead slot lines): same results as the oracle, forward and inverse."""
+    from saclaymocks_b200 import _lib
     from saclaymocks_b200.boxes import BoxSynth, PRODUCTS, WEIGHT_OF
-    monkeypatch.setenv("SMK_YZ_GROUP", str(group))
-    monkeypatch.setenv("SMK_YZ_STREAMS", str(streams))
     NX, NY, NZ, dcell = 32, 64, 96, 4.0
     W, noise, raw, p0, boxes, sig = _oracle_run(NX, NY, NZ, dcell, 42)
-    bs = BoxSynth(NX, NY, NZ, dcell, device=cuda)
+    with _lib.option("yz_group", group), _lib.option("yz_streams", streams):      # read when the context is created
+        bs = BoxSynth(NX, NY, NZ, dcell, device=cuda)
     boxk = bs.draw_grf_boxk(noise=torch.as_tensor(noise, device=cuda))
     assert rel_l2(bs.boxk_to_numpy(boxk), raw) < TOL
     Wd = {k: bs.upload_weights(v) for k, v in W.items()}

@@ -150,7 +150,7 @@ def test_gpu_fast_kernel_probability_matches_oracle_ptot(cuda):
     bs.close()
 
 
-def test_gpu_fast_kernel_selects_the_exact_kernels_quasars(cuda, monkeypatch):
+def test_gpu_fast_kernel_selects_the_exact_kernels_quasars(cuda):
     """Production kernel (tabulated float32 ptot) against the reference-arithmetic kernel on the SAME Philox variates
     (both take cond1's variate from cond1_block(), smk_qso.cu): the two selections are identical except for cells
     whose variate falls inside the float32 / table error of norm * ptot (relative 1e-4: a handful out of ~1e4 cond1
@@ -169,9 +169,9 @@ def test_gpu_fast_kernel_selects_the_exact_kernels_quasars(cuda, monkeypatch):
     d = qso.QsoDrawer(bs)
     a = ([dev["boxln_1"], dev["boxln_2"], dev["boxln_3"]], [dev["vx"], dev["vy"], dev["vz"]])
     fast = d.draw(st, *a, ix0=NXs, seed=21)
-    monkeypatch.setenv("SMK_QSO_EXACT", "1")
-    exact = d.draw(st, *a, ix0=NXs, seed=21)
-    monkeypatch.delenv("SMK_QSO_EXACT")
+    from saclaymocks_b200 import _lib
+    with _lib.option("qso_exact", 1):
+        exact = d.draw(st, *a, ix0=NXs, seed=21)
     kf = {tuple(c): i for i, c in enumerate(fast["cells"])}
     ke = {tuple(c): i for i, c in enumerate(exact["cells"])}
     common = sorted(set(kf) & set(ke))

@@ -220,15 +220,15 @@ def test_smallscale_and_fgpa_vs_oracle(cuda):
         assert np.all(F[:, -100:] == 1.0)
 
 
-def test_register_blocked_kernel_equals_simple_kernel(cuda, golden_ref32, monkeypatch):
+def test_register_blocked_kernel_equals_simple_kernel(cuda, golden_ref32):
     """The P-pixels-per-thread gather (union window) against the one-pixel-per-thread kernel on the same input."""
     from saclaymocks_b200 import spectra as sp
     g = golden_ref32
     rng = np.random.default_rng(3)
     boxes = {k: rng.standard_normal((32, 32, 1536), dtype=np.float32) for k in sp.FIELDS}
-    monkeypatch.setenv("SMK_SKEWERS_SIMPLE", "1")
-    _, _, _, _, simple = _gpu_skewers(g, boxes, cuda, slabs=2)
-    monkeypatch.delenv("SMK_SKEWERS_SIMPLE")
+    from saclaymocks_b200 import _lib
+    with _lib.option("skewers_kernel", 2):
+        _, _, _, _, simple = _gpu_skewers(g, boxes, cuda, slabs=2)
     _, _, _, _, multi = _gpu_skewers(g, boxes, cuda, slabs=2)
     for a, b, tol in zip(simple, multi, (3e-6, 3e-6, 3e-6)):
         a, b = a.cpu().numpy(), b.cpu().numpy()
@@ -238,7 +238,7 @@ def test_register_blocked_kernel_equals_simple_kernel(cuda, golden_ref32, monkey
         assert np.max(np.abs(a[m] - b[m])) < tol
 
 
-def test_staged_gather_equals_global_memory_gather(cuda, monkeypatch):
+def test_staged_gather_equals_global_memory_gather(cuda):
     """The TMA-staged kernel (boxes of cells in shared memory) against the global-memory kernel on the same input:
     the same walk over the same values (agreement to the last bits: 2e-6; the two kernels instantiate the walk
     separately, so the compiler may contract a multiply-add differently); most segments must really be staged."""
@@ -260,10 +260,9 @@ def test_staged_gather_equals_global_memory_gather(cuda, monkeypatch):
         staged = eng.read_spec(boxes, xyzr, nfor, rsd=rsd, dla=dla)
         seg, back, box = _lib.skewers_stats()
         assert seg > 0 and back < 0.25 * seg, (seg, back, box)                  # the staged kernel did the work
-        monkeypatch.setenv("SMK_SKEWERS_STAGED", "0")
-        plain = eng.read_spec(boxes, xyzr, nfor, rsd=rsd, dla=dla)
-        assert _lib.skewers_stats()[0] == 0
-        monkeypatch.delenv("SMK_SKEWERS_STAGED")
+        with _lib.option("skewers_kernel", 1):
+            plain = eng.read_spec(boxes, xyzr, nfor, rsd=rsd, dla=dla)
+            assert _lib.skewers_stats()[0] == 0
         for a, b in zip(staged, plain):
             assert torch.equal(torch.isnan(a), torch.isnan(b))
             assert float((torch.nan_to_num(a, nan=-7.0) - torch.nan_to_num(b, nan=-7.0)).abs().max()) < 2e-6

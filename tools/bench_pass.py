@@ -21,5 +21,5 @@ for name, wt in (("eta_xy", None), ("boxln_1", W)):
     nk = NX * NY * (NZ // 2 + 1) * 8
     mult = {"inv_yz": 4, "fwd_zy": 3}      # chained pairs: bytes of both passes under the 24 B/cell model
     tot = sum(ms / n for ms, n in t.values() if n)
-    print(os.environ.get("SMK_YZ_GROUP", "0"), os.environ.get("SMK_YZ_STREAMS", "-"), name, "total %.3f ms" % tot,
+    print(name, "total %.3f ms" % tot,
           {k: "%.3f ms %.0f GB/s" % (ms / n, mult.get(k, 2) * nk / (ms / n * 1e-3) / 1e9) for k, (ms, n) in t.items() if n})

@@ -86,7 +86,8 @@ def main():
         if world > 1:
             dist.all_reduce(tot)
         res.append({"chunk": c, "window": [ra0, dra, dec0, ddec], "nqso": int(len(cat["RA"])), "home_rows": int(tot[0]),
-                    "forest_pixels": int(tot[2]), "t_chunk_s": t_chunk, "t_gather_rows_s": t_gather,
+                    "forest_pixels": int(tot[2]), "t_chunk_s": t_chunk, "phases_s_rank0": pipe.last_chunk_timings,
+                    "t_gather_rows_s": t_gather,
                     "t_write_sample_s": t_write, "transmission_files_rank0": int(nfiles or 0),
                     "sigma_box": pipe.sigmas()["box"], "checks": checks})
         if rank == 0:
