@@ -608,6 +608,11 @@ int launch_r2c_z(int NZ, const float* in, float2* out, long long nlines, int pit
   return SMK_ERR_UNSUPPORTED;
 }
 
+// (A persistent form of this pass with bulk-copy tile loads -- cp.async.bulk of the 50 KB tile into a staging buffer
+// under an mbarrier while the previous tile's butterflies run, two CTAs of 192 threads per SM -- was built and measured
+// in round 2: parity green, 0.958 ms against 0.772 ms.  The pass is bound by instruction issue and shared-memory
+// traffic inside the SM, not by exposed DRAM latency: the staging hop and the smaller number of resident warps cost
+// more than the overlap gains.  profiles/README.md.)
 template <int M>
 static int launch_c2r_t(const C2RParams& p, cudaStream_t st) {
   size_t smem = (size_t)ZTraits<M>::LINES * C2RTraits<M>::LP * sizeof(float2);
