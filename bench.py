@@ -517,9 +517,18 @@ def run_gpu(args):
         # copy peak + 14 exchanges of (N-1)/N of this rank's half-complex box at the measured 770 GB/s per direction
         t_hbm = 332.0 * cells / world / (peak * 1e9) * 1e3
         t_nvl = 14 * (world - 1) / world * nk_bytes / 770e9 * 1e3
+        # A rank's box interval also holds its wait for the ranks that are still in the previous step's skewers (the box
+        # stage runs in lock step): the rank with the fullest slab never waits, so the smallest interval is the box stage
+        t_box_true = min(box_r)
+        t_skw_model = SKEWER_BYTES_PER_PIXEL * max(pix_r) / (peak * 1e9) * 1e3
         roofline["boxes_model_ms"] = {"hbm": t_hbm, "nvlink": t_nvl, "serial": t_hbm + t_nvl, "overlapped": max(t_hbm, t_nvl),
-                                      "frac_serial": (t_hbm + t_nvl) / max(box_r),
-                                      "frac_overlapped": max(t_hbm, t_nvl) / max(box_r)}
+                                      "t_boxes_ms_without_waiting": t_box_true,
+                                      "frac_serial": (t_hbm + t_nvl) / t_box_true,
+                                      "frac_overlapped": max(t_hbm, t_nvl) / t_box_true}
+        roofline["chunk_model_ms"] = {"boxes_serial": t_hbm + t_nvl, "skewers_hbm_fullest_slab": t_skw_model,
+                                      "frac_of_step": (t_hbm + t_nvl + t_skw_model) / t_tot,
+                                      "what": "combined HBM/NVLink roofline of the chunk (serial model of the box stage + "
+                                              "byte model of the fullest slab's skewers) over the measured step"}
         roofline["note"] = ("N > 1: the x pass runs on a second stream against the y / z passes of the previous product, "
                             "so the per-pass intervals overlap and each is inflated by the other stream's kernels; the "
                             "single-GPU line carries the per-kernel roofline")

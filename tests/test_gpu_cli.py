@@ -119,3 +119,48 @@ def test_draw_qso_cli_matches_reference_files(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(BIN, "draw_qso.py"), "-indir", boxes, "-outpath", out, "-i", "0",
                         "-Nslice", str(ns), "-desi", "True"], capture_output=True, text=True)
     assert r.returncode != 0 and "not supported" in r.stdout          # fails loudly instead of silently skipping
+
+
+def test_make_boxes_and_make_spectra_under_torchrun(tmp_path, golden_small):
+    """The reference's CLIs on two GPUs: `torchrun bin/make_boxes.py` (box sharded over the ranks, every rank writes the
+    files of its planes, weight tables evaluated on the GPU) and `torchrun bin/make_spectra.py` without -i (slices dealt
+    to the ranks) write the same files as the reference run (tests/golden/ref_small.npz)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from saclaymocks_b200 import fitsio_lite as fitsio
+    g = golden_small
+    NX, NY, NZ, dcell, ns = int(g["NX"]), int(g["NY"]), int(g["NZ"]), float(g["dcell"]), int(g["nslice"])
+    d = {k: str(tmp_path / k) for k in ("boxes", "qso", "spectra")}
+    for v in d.values():
+        os.makedirs(v)
+
+    def torchrun(script, *argv):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+               "127.0.0.1", "--master-port", "29533", os.path.join(BIN, script)] + [str(a) for a in argv]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        return r.stdout
+
+    torchrun("make_boxes.py", "-NX", NX, "-NY", NY, "-NZ", NZ, "-pixel", dcell, "-nHDU", ns, "-PkDir", "gpu", "-seed",
+             int(g["seed"]), "-rsd", "True", "-outDir", d["boxes"], "-noise", "mt19937")
+    for name, n in (("boxln_1", ns), ("boxln_2", ns), ("boxln_3", ns), ("vx", ns), ("vy", ns), ("vz", ns), ("box", NX),
+                    ("eta_xx", NX), ("eta_yy", NX), ("eta_zz", NX), ("eta_xy", NX), ("eta_xz", NX), ("eta_yz", NX)):
+        files = [d["boxes"] + "/%s-%d.fits" % (name, i) for i in range(n)]
+        assert len(glob.glob(d["boxes"] + "/%s-*.fits" % name)) == n
+        box = np.concatenate([fitsio.read(f) for f in files])
+        assert rel_l2(box, g["box_" + name]) < 1e-5, name
+        h = fitsio.read_header(files[0])
+        assert (h["NX"], h["NY"], h["NZ"], h["DX"]) == (NX, NY, NZ, dcell)
+        assert abs(h["sigma"] / float(g["sigma_" + name]) - 1) < 1e-4 and h["seed"] == int(g["seed"])
+    assert len(glob.glob(d["boxes"] + "/boxk-*of2.npy")) == 2
+    write_qso_files(g, d["qso"])
+    torchrun("make_spectra.py", "-QSOfile", d["qso"] + "/QSO-", "-boxdir", d["boxes"], "-outDir", d["spectra"], "-N", ns,
+             "-zmin", 1.8, "-zmax", 3.6, "-rsd", "True", "-dla", "True")
+    ref_files = sorted(k[:-len("_THING_ID")] for k in g if k.startswith("spectra_") and k.endswith("_THING_ID"))
+    got_files = sorted(os.path.basename(f).split(".")[0].replace("-", "_") for f in glob.glob(d["spectra"] + "/*.gz"))
+    assert got_files == ref_files
+    for key in ref_files:
+        f = fitsio.FITS(d["spectra"] + "/" + key.replace("_", "-") + ".fits.gz")
+        assert np.array_equal(f["METADATA"].read()["THING_ID"], g[key + "_THING_ID"])
+        for ext, tol in (("DELTA_L", 1e-5), ("ETA_PAR", 1e-5), ("VELO_PAR", 2e-2)):
+            assert np.max(np.abs(f[ext].read() - g[key + "_" + ext])) < tol, (key, ext)
