@@ -58,8 +58,9 @@ class ChunkPipeline(object):
         self.cat = None
         self.footprint = None
         self._qso_setup = None
-        # kernels per step: 3 forward passes + 13 x 3 inverse passes + small-scale + gather (FGPA in its epilogue)
-        self.launches_per_step = 3 + 13 * 3 + (2 if os.environ.get("SMK_FUSED_FGPA", "1") != "0" else 3)
+        # kernels of this library per step: 3 forward passes + 13 x 3 inverse passes + small-scale field + per box class of
+        # the catalogue (set_catalogue) the gather's four kernels: sentinels, work list, staged gather, hand-back walk
+        self.launches_per_step = 3 + 13 * 3 + 1 + 4
 
     def _connect_exchange(self):
         """Fused exchange set-up: two receive buffers per rank, mapped into every peer through CUDA IPC."""
@@ -144,6 +145,7 @@ class ChunkPipeline(object):
         hi = np.where(zero, npix if xmin < 0 <= xmax else 0, hi)
         own = int(np.clip(np.minimum(hi, cn) - lo, 0, None).sum())
         self.cat["own_pixels"] = own
+        self.launches_per_step = 3 + 13 * 3 + 1 + 4 * len(groups) + (0 if os.environ.get("SMK_FUSED_FGPA", "1") != "0" else 1)
 
     def forest_pixels_total(self):
         t = torch.tensor([self.cat["own_pixels"]], dtype=torch.int64, device=self.device)
