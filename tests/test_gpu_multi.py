@@ -21,8 +21,8 @@ def _worker(rank, world, port, shape, dcell, out, p2p, xsms=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["SMK_P2P"] = p2p
-    if xsms:
-        os.environ["SMK_X_SMS"] = str(xsms)      # persistent fused-exchange x pass on that many CTAs
+    os.environ["SMK_X_SMS"] = str(xsms)          # fused-exchange x pass: one CTA per tile (0) or persistent on that many
+                                                 # CTAs (the default of 8 ranks, 96, is what bench.py's self-check runs)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
