@@ -73,3 +73,19 @@ def test_product_refuses_to_run_without_cuda():
     from saclaymocks_b200.boxes import BoxSynth
     with pytest.raises(_lib.SmkError):
         BoxSynth(16, 16, 24, 2.19)
+
+
+def test_options_and_light_context_need_no_gpu():
+    """smk_set_option / smk_ctx_create_light are host-side only: usable (and checked) without a device."""
+    from saclaymocks_b200 import _lib
+    L = _lib.lib()
+    assert L.smk_set_option(b"skewers_kernel", 1) == 0 and L.smk_set_option(b"skewers_kernel", 0) == 0
+    assert L.smk_set_option(b"no_such_option", 1) != 0
+    assert b"unknown option" in L.smk_last_error()
+    with _lib.option("qso_exact", 1):
+        pass
+    h = ctypes.c_void_p()
+    assert L.smk_ctx_create_light(ctypes.byref(h), None) == 0 and h.value
+    assert L.smk_boxk_pitch(h) == 0                      # no FFT plan behind a light context
+    assert L.smk_exchange_create(h, 2) != 0              # ... and the box entry points refuse it
+    assert L.smk_ctx_destroy(h) == 0
