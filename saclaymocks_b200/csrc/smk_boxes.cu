@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "smk_fft.cuh"
+#include "smk_ztile.cuh"
 #include "smk_internal.h"
 #include "smk_philox.cuh"
 
@@ -74,6 +75,9 @@ enum { OUT_PLAIN = 0, OUT_SPLIT = 1, OUT_PEER = 2 };
 // Fused-multiply x passes (measured at 512 x 512 x 1536, tools/x_sweep.sh): the k-factor variants (eta, velocity) load
 // their first-stage tasks two at a time, which fits 80 registers = 3 CTAs per SM (0.738 -> 0.702 ms); the table variant
 // needs the weights as well, spills at 80 registers (0.870 -> 0.914 ms) and keeps all loads in flight at 2 CTAs per SM.
+#ifndef SMK_VEL_F64
+#define SMK_VEL_F64 0     // 1: velocity factor in real float64 arithmetic (the first implementation, kept for A/B runs)
+#endif
 #ifndef SMK_MUL_BATCH
 #define SMK_MUL_BATCH 2   // first-stage tasks loaded together in the k-factor passes (0 = all)
 #endif
@@ -133,10 +137,25 @@ __device__ __forceinline__ void strided_tile(const StridedParams& p, const int t
       return make_float2(__fmul_rn(v.x, f), __fmul_rn(v.y, f));
     }
     // MUL_VEL: boxk *= -1j*k/kk*H0*dgrowth0 -- float32 up to "*H0", then float64 (numpy promotes on the float64
-    // scalar dgrowth0 and rounds the complex128 product back to complex64)
+    // scalar dgrowth0 and rounds the complex128 product back to complex64).  The float64 product is formed as an
+    // unevaluated float32 pair instead (f = fh + fl to 2^-48, v * f = p + t), rounded once at the end: the same float32
+    // as numpy's unless the exact product lies within ~2^-46 of a rounding boundary (none in 2e7 random samples), at
+    // 11 FP32 instructions per element instead of 5 float32 <-> float64 conversions and 3 DMUL, which made this variant
+    // issue-bound on the conversion pipe (0.90 ms against 0.64 ms for the eta variant).
+#if SMK_VEL_F64
     const float f32 = __fmul_rn(fdiv_fast(-ka, kk, rcp_approx(kk)), 100.0f);
     const double f = (double)f32 * p.mul.vscale;
     return make_float2((float)(-(double)v.y * f), (float)((double)v.x * f));
+#else
+    const float f32 = __fmul_rn(fdiv_fast(-ka, kk, rcp_approx(kk)), 100.0f);
+    const float fh = __fmul_rn(f32, p.mul.vs_hi);
+    const float fl = __fmaf_rn(f32, p.mul.vs_lo, __fmaf_rn(f32, p.mul.vs_hi, -fh));
+    auto times_f = [&](float a) {
+      const float pr = __fmul_rn(a, fh);
+      return __fadd_rn(pr, __fmaf_rn(a, fl, __fmaf_rn(a, fh, -pr)));
+    };
+    return make_float2(-times_f(v.y), times_f(v.x));
+#endif
   };
   auto st_g = [&](int, int k, float2 val) { outl[point_off<SPLIT_OUT == OUT_SPLIT>(p.aout, k)] = val; };
   auto st_s = [&](int line, int pos, float2 val) { sm[pos * LINES + line] = val; };
@@ -281,6 +300,8 @@ int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, floa
   make_fastdiv(ain);
   make_fastdiv(aout);
   StridedParams p{in, out, ain, aout, ncols, wcols, mul, tw, {nullptr}, nouter, x_sms};
+  p.mul.vs_hi = (float)mul.vscale;                                 // dgrowth0 as a float32 pair (MUL_VEL)
+  p.mul.vs_lo = (float)(mul.vscale - (double)p.mul.vs_hi);
   if (peers) {
     if (npeers > SMK_MAX_RANKS) { set_error("too many ranks for the fused exchange"); return SMK_ERR_ARG; }
     for (int i = 0; i < npeers; ++i) p.peer[i] = peers[i];
@@ -294,85 +315,6 @@ int launch_c2c_strided(int N, bool inverse, int mul_mode, const float2* in, floa
   return SMK_ERR_UNSUPPORTED;
 }
 
-// ------------------------------------------------------------------ contiguous (z) pass
-template <int M>
-struct ZTraits {
-  using P = typename PlanFor<M>::type;
-#ifndef SMK_Z_LINES
-#define SMK_Z_LINES 8    // lines per tile of the NZ = 1536 z passes: 8 = four CTAs of 128 threads and 50 KB per SM, whose
-#endif                   // load / transform / store phases interleave better than those of two 16-line CTAs (measured on
-                         // B200, tools/z_lines_check.sh: c2r z 0.787 -> 0.772 ms, r2c z + Philox 1.186 -> 1.147 ms)
-  static constexpr int LINES = (M > 1024) ? 4 : ((M == 768) ? SMK_Z_LINES : 16);
-  static constexpr int NT_ = (M % 3 == 0) ? LINES * M / 48 / 32 * 32 : LINES * M / 32;
-  static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
-  // PERM: two-stage plan R0.R1 with a radix-32 first stage, run without the re-sorting last stage (which would need
-  // all of a thread's butterflies in registers at once).  Natural index k then sits at position (k % R0) R1 + k / R0;
-  // with one float2 of padding after every R1 points, consecutive k are 25 float2 apart for R1 = 24: the permuted
-  // reads of the store / post-processing loops (lane = k) stay free of bank conflicts.
-  static constexpr bool PERM = (P::S == 2 && P::radix(0) >= 32);
-  static constexpr int R0 = P::radix(0), R1 = PERM ? P::radix(1) : 1;
-  static constexpr int LP_ = PERM ? M + M / R1 : M;
-  // pitch: the lanes of a half-warp are LINES lines x 16 / LINES consecutive positions of one stage; with a pitch of
-  // 16 / LINES (mod 16) float2 they fall on 16 different bank pairs (LINES == 16: any odd pitch)
-  static constexpr int pitch(int least) {
-    int lp = least;
-    while (lp % 16 != (16 / LINES) % 16) ++lp;
-    return lp;
-  }
-  static constexpr int LP = (LINES == 16) ? LP_ + 1 - LP_ % 2 : pitch(LP_);
-  __device__ static __forceinline__ int idx(int p) { return PERM ? p + p / R1 : p; }         // padded position
-  __device__ static __forceinline__ int nat(int k) { return PERM ? idx((k % R0) * R1 + k / R0) : k; }   // where output k sits
-};
-
-// the M-point transform of every line of the tile in shared memory ([line][idx(point)], pitch LP); natural-order input.
-// Output k of a line ends at ZTraits<M>::nat(k).
-template <int M, bool INV>
-__device__ __forceinline__ void z_tile_fft(float2* sm, const float2* __restrict__ tw) {
-  using ZT = ZTraits<M>;
-  using P = typename ZT::P;
-  constexpr int LINES = ZT::LINES, NT = ZT::NT, LP = ZT::LP;
-  if constexpr (ZT::PERM) {
-    auto ld = [&](int line, int pos, int, int) { return sm[line * LP + ZT::idx(pos)]; };
-    auto st = [&](int line, int pos, float2 val) { sm[line * LP + ZT::idx(pos)] = val; };
-    dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 1>(ld, st, tw, 2);
-    __syncthreads();
-    dif_stage<P, 1, INV, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 1>(ld, st, tw, 2);
-    __syncthreads();
-  } else {
-    dif_stages_smem<P, 0, P::S - 1, INV, LINES, LP, 1, NT>(sm, tw, 2);
-    dif_last_resort_smem<P, INV, LINES, LP, 1, NT>(sm, tw, 2);
-  }
-}
-
-// Inverse z pass with the last DIF stage fused into the store (plans of >= 2 stages): the last stage has no twiddles and
-// its butterfly b = pos(n0) / RL produces the natural outputs n0 + q M/RL, so a warp whose lanes take CONSECUTIVE n0
-// runs it straight from shared memory into coalesced global stores -- the re-sort (one shared-memory write + read of
-// the tile) and the separate store loop's read disappear (8 -> 6 passes over the tile in shared memory; the kernel is
-// bound by that pipe).  Consecutive n0 read positions M/R0 apart: one float2 of padding after every M/R0 positions
-// makes that stride odd in units of 8 bytes, i.e. conflict free for the 16 lanes of a half-warp.
-template <int M>
-struct C2RTraits {
-  using ZT = ZTraits<M>;
-  using P = typename ZT::P;
-  static constexpr int R0 = P::radix(0), RL = P::radix(P::S - 1), BLK = M / R0, NB = M / RL;
-  static constexpr bool FUSE = (P::S >= 2) && !ZT::PERM && (BLK % 2 == 0) && (BLK % RL == 0) && (M >= 32);
-  static constexpr int LP_ = M + R0;
-  static constexpr int LP = FUSE ? (ZT::LINES == 16 ? (LP_ + 1 - LP_ % 2) : ZT::pitch(LP_)) : ZT::LP;
-  __device__ static __forceinline__ int idx(int p) { return FUSE ? p + p / BLK : ZT::idx(p); }
-};
-
-// stages [S0, S1) in place through the padded index, a barrier after each
-template <class CT, int S0, int S1, int LINES, int NT, int LP>
-__device__ __forceinline__ void c2r_stages(float2* sm, const float2* __restrict__ tw) {
-  if constexpr (S0 < S1) {
-    auto ld = [&](int line, int ppos, int, int) { return sm[line * LP + ppos]; };          // padded positions
-    auto st = [&](int line, int ppos, float2 val) { sm[line * LP + ppos] = val; };
-    dif_stage<typename CT::P, S0, true, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, CT::BLK>(ld, st, tw, 2);
-    __syncthreads();
-    c2r_stages<CT, S0 + 1, S1, LINES, NT, LP>(sm, tw);
-  }
-}
-
 struct R2CParams {
   const float* in;
   float2* out;
@@ -384,7 +326,8 @@ struct R2CParams {
 };
 
 template <int M, bool PHILOX>
-__global__ void __launch_bounds__(ZTraits<M>::NT) r2c_z_kernel(R2CParams p) {
+// (as for c2r_z_kernel: four 8-line CTAs per SM at NZ = 1536 need 128 registers or fewer)
+__global__ void __launch_bounds__(ZTraits<M>::NT, (M == 768) ? 32 / ZTraits<M>::LINES : 1) r2c_z_kernel(R2CParams p) {
   using ZT = ZTraits<M>;
   constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = ZTraits<M>::LP;
   extern __shared__ float2 sm[];   // [LINES][LP]
@@ -462,20 +405,23 @@ __global__ void __launch_bounds__(ZTraits<M>::NT, (M >= 512) ? 32 / ZTraits<M>::
   //      A = X[k] + conj(X[M-k]), B = (X[k] - conj(X[M-k])) w^-k.  The imaginary parts of the DC and Nyquist bins
   //      are ignored, as FFTW's / pocketfft's c2r do.
   constexpr int KI = (M / 2 + 1 + 31) / 32;   // (k, M-k) pairs per lane and line
+  float2 w[KI];                               // w^k of the lane's k: the same for every line of the warp
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    const int k = (threadIdx.x & 31) + 32 * i;
+    w[i] = (k <= M / 2) ? __ldg(p.tw + k) : make_float2(0.f, 0.f);
+  }
   for (int line = threadIdx.x >> 5; line < LINES; line += NT / 32) {
     const bool ok = line0 + line < p.nlines;
     const float2* src = p.in + (line0 + line) * p.pitch;
     float2* row = sm + line * LP;
     // all loads of the line first (2*KI independent 8-byte loads per lane in flight), arithmetic afterwards
-    float2 a[KI], b[KI], w[KI];
+    float2 a[KI], b[KI];
 #pragma unroll
     for (int i = 0; i < KI; ++i) {
       const int k = (threadIdx.x & 31) + 32 * i;
-      a[i] = b[i] = w[i] = make_float2(0.f, 0.f);
-      if (k <= M / 2) {
-        w[i] = __ldg(p.tw + k);
-        if (ok) { a[i] = __ldg(src + k); b[i] = __ldg(src + M - k); }
-      }
+      a[i] = b[i] = make_float2(0.f, 0.f);
+      if (k <= M / 2 && ok) { a[i] = __ldg(src + k); b[i] = __ldg(src + M - k); }
     }
 #pragma unroll
     for (int i = 0; i < KI; ++i) {
@@ -515,11 +461,8 @@ __global__ void __launch_bounds__(ZTraits<M>::NT, (M >= 512) ? 32 / ZTraits<M>::
         const float2* row = sm + line * LP;
 #pragma unroll 2
         for (int n0 = threadIdx.x & 31; n0 < NB; n0 += 32) {
-          const int pb = P::pos(n0);
           float2 v[RL];
-#pragma unroll
-          for (int t = 0; t < RL; ++t) v[t] = row[CT::idx(pb + t)];
-          Butterfly<RL, true>::run(v);
+          c2r_last_butterfly<CT>(row, n0, v);
 #pragma unroll
           for (int q = 0; q < RL; ++q) {
             float2 z = v[q];

@@ -358,6 +358,33 @@ SMK_PLAN(2560, 16, 16, 2, 5)
 SMK_PLAN(4096, 16, 16, 16)
 #undef SMK_PLAN
 
+// ---------------------------------------------------------------- compile-time twiddles
+// cos / sin of 2 pi num / den evaluated in constant expressions (double Taylor series after reduction to [-pi, pi]:
+// absolute error below 1e-15, i.e. exact after rounding to float except for rare ties).
+__host__ __device__ constexpr double cx_cos_sin(long long num, long long den, bool want_sin) {
+  num %= den;
+  if (2 * num > den) num -= den;
+  const double x = 6.283185307179586476925286766559 * (double)num / (double)den, x2 = x * x;
+  double term = want_sin ? x : 1.0, sum = term;
+  for (int k = want_sin ? 1 : 0; k < 44; k += 2) {
+    term *= -x2 / (double)((k + 1) * (k + 2));
+    sum += term;
+  }
+  return sum;
+}
+// c[i][q], s[i][q] = cos, sin of 2 pi (q i STEP) / L for i < T, q < R
+template <int L, int STEP, int T, int R>
+struct TwConst {
+  float c[T][R], s[T][R];
+  __host__ __device__ constexpr TwConst() : c{}, s{} {
+    for (int i = 0; i < T; ++i)
+      for (int q = 0; q < R; ++q) {
+        c[i][q] = (float)cx_cos_sin((long long)q * i * STEP, L, false);
+        s[i][q] = (float)cx_cos_sin((long long)q * i * STEP, L, true);
+      }
+  }
+};
+
 // ---------------------------------------------------------------- one DIF stage
 // Tile element (line, pos) is accessed through the functors:
 //   ld(line, pos)        -> float2     (input position, pre-stage)
@@ -381,8 +408,19 @@ struct NoPre {
 // PADBLK > 0 (in-place stages only): the tile is stored with one element of padding after every PADBLK = N / R0
 // positions (position p at p + p / PADBLK); the stage hands ld / st the PADDED position, computed from the block index
 // once per butterfly instead of a division per element.
+// TW selects where the twiddles W_sub^(o q) of a non-final stage come from.  With several lines per warp the lanes of
+// a table load read a few scattered addresses (one per butterfly offset o), each its own L1 wavefront, which on the
+// shared-memory-bound z passes costs as much as the data:
+//   TW_TABLE  one table load per output and task (the general case);
+//   TW_SPLIT  (stage 0, where o = j0 + i JSTEP for the thread's task i) one load W^(q j0) per output, shared by the
+//             thread's tasks: task i multiplies it by the compile-time constant W^(q i JSTEP);
+//   TW_CONST  the thread takes the MQ butterflies of ONE block b = j0 (o = i is a compile-time value): no loads at
+//             all.  Needs MQ tasks per thread; tasks of neighbouring threads are then a whole sub-transform apart, so
+//             the tile needs the padded layout to stay free of bank conflicts.
+enum { TW_TABLE = 0, TW_SPLIT = 1, TW_CONST = 2 };
+
 template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store, class Pre = NoPre,
-          int BATCH = 0, int PADBLK = 0>
+          int BATCH = 0, int PADBLK = 0, int TW = TW_TABLE>
 __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __restrict__ tw, int twmul,
                                           Pre pre = Pre()) {
   constexpr int R = P::radix(STAGE);
@@ -405,49 +443,100 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
   constexpr int TPAD = (PADBLK > 0 && STAGE == 0) ? 1 : 0;
   constexpr bool EVEN = (NTASK % NT == 0);
   constexpr int JSTEP = NT / LINES;
+  static_assert(TW != TW_SPLIT || (STAGE == 0 && !LAST), "split twiddles: first stage of a multi-stage plan");
+  static_assert(TW != TW_CONST || (!LAST && EVEN && TB == TPT && TPT == MQ && NB == JSTEP * MQ),
+                "constant twiddles: one block of MQ butterflies per thread");
   // a thread always works on the same line: task = threadIdx.x + i*NT  =>  line = threadIdx.x % LINES
   const int line = threadIdx.x % LINES;
   const int j0 = threadIdx.x / LINES;
+  // butterfly index of the thread's task i
+  auto task_j = [&](int i) { return TW == TW_CONST ? j0 * MQ + i : j0 + i * JSTEP; };
+  auto task_base = [&](int b, int o) {
+    return b * M + o + ((PADBLK > 0 && STAGE > 0) ? b / (PADBLK > 0 ? PADBLK / M : 1) : 0);
+  };
 #pragma unroll
   for (int i0 = 0; i0 < TPT; i0 += TB) {
     // phase 1: the loads of this batch (keeps TB*R independent loads in flight)
     float2 v[TB][R];
 #pragma unroll
     for (int ii = 0; ii < TB; ++ii) {
-      const int j = j0 + (i0 + ii) * JSTEP;
+      const int j = task_j(i0 + ii);
       if (i0 + ii < TPT && (EVEN || j < NB)) {
         const int b = j / MQ, o = j - b * MQ;
-        const int base = b * M + o + ((PADBLK > 0 && STAGE > 0) ? b / (PADBLK > 0 ? PADBLK / M : 1) : 0);
+        const int base = task_base(b, o);
 #pragma unroll
         for (int t = 0; t < R; ++t) v[ii][t] = ld(line, base + t * (MQ + TPAD), ii, t);
       }
     }
     if (OUT == OUT_RESORT) __syncthreads();
+    if constexpr (TW == TW_SPLIT) {
+      // all butterflies, then output q of every task from ONE table load, then the stores
 #pragma unroll
-    for (int ii = 0; ii < TB; ++ii) {
-      const int j = j0 + (i0 + ii) * JSTEP;
-      if (i0 + ii < TPT && (EVEN || j < NB)) {
-        const int b = j / MQ, o = j - b * MQ;
+      for (int ii = 0; ii < TB; ++ii) {
+        const int j = task_j(i0 + ii);
+        if (i0 + ii < TPT && (EVEN || j < NB)) {
 #pragma unroll
-        for (int t = 0; t < R; ++t) v[ii][t] = pre(line, b * M + o + t * MQ, ii, t, v[ii][t]);
-        Butterfly<R, INV>::run(v[ii]);
-        if (!LAST) {
-          const int oc = o * ((P::N / M) * twmul);   // W_sub^(o q) = W_L[q * oc]
+          for (int t = 0; t < R; ++t) v[ii][t] = pre(line, j + t * MQ, ii, t, v[ii][t]);
+          Butterfly<R, INV>::run(v[ii]);
+        }
+      }
+      constexpr TwConst<P::N, JSTEP, TPT, R> K{};   // W_N^(q i JSTEP)
+      const int oc = j0 * twmul;                    // W_N^(q j0) = W_L[q j0 twmul]
 #pragma unroll
-          for (int q = 1; q < R; ++q) {
-            float2 w = __ldg(tw + q * oc);
-            if (INV) w.y = -w.y;
-            v[ii][q] = cmul(v[ii][q], w);
+      for (int q = 1; q < R; ++q) {
+        float2 w = __ldg(tw + q * oc);
+        if (INV) w.y = -w.y;
+#pragma unroll
+        for (int ii = 0; ii < TB; ++ii) {
+          if (i0 + ii < TPT && (EVEN || task_j(i0 + ii) < NB)) {
+            const float2 wi = (i0 + ii == 0) ? w : twc<INV>(w, K.c[i0 + ii][q], K.s[i0 + ii][q]);
+            v[ii][q] = cmul(v[ii][q], wi);
           }
         }
-        if (OUT != OUT_INPLACE) {
-          const int nb = P::nat(b * M);
+      }
 #pragma unroll
-          for (int q = 0; q < R; ++q) st(line, nb + q * (P::N / R), v[ii][q]);
-        } else {
-          const int base = b * M + o + ((PADBLK > 0 && STAGE > 0) ? b / (PADBLK > 0 ? PADBLK / M : 1) : 0);
+      for (int ii = 0; ii < TB; ++ii) {
+        const int j = task_j(i0 + ii);
+        if (i0 + ii < TPT && (EVEN || j < NB)) {
 #pragma unroll
-          for (int q = 0; q < R; ++q) st(line, base + q * (MQ + TPAD), v[ii][q]);
+          for (int q = 0; q < R; ++q) st(line, j + q * (MQ + TPAD), v[ii][q]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int ii = 0; ii < TB; ++ii) {
+        const int j = task_j(i0 + ii);
+        if (i0 + ii < TPT && (EVEN || j < NB)) {
+          const int b = j / MQ, o = j - b * MQ;
+#pragma unroll
+          for (int t = 0; t < R; ++t) v[ii][t] = pre(line, b * M + o + t * MQ, ii, t, v[ii][t]);
+          Butterfly<R, INV>::run(v[ii]);
+          if (!LAST) {
+            if constexpr (TW == TW_CONST) {
+              constexpr TwConst<M, 1, MQ, R> K{};   // W_sub^(q o), o = i0 + ii
+              if (i0 + ii > 0) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[ii][q] = twc<INV>(v[ii][q], K.c[i0 + ii][q], K.s[i0 + ii][q]);
+              }
+            } else {
+              const int oc = o * ((P::N / M) * twmul);   // W_sub^(o q) = W_L[q * oc]
+#pragma unroll
+              for (int q = 1; q < R; ++q) {
+                float2 w = __ldg(tw + q * oc);
+                if (INV) w.y = -w.y;
+                v[ii][q] = cmul(v[ii][q], w);
+              }
+            }
+          }
+          if (OUT != OUT_INPLACE) {
+            const int nb = P::nat(b * M);
+#pragma unroll
+            for (int q = 0; q < R; ++q) st(line, nb + q * (P::N / R), v[ii][q]);
+          } else {
+            const int base = task_base(b, o);
+#pragma unroll
+            for (int q = 0; q < R; ++q) st(line, base + q * (MQ + TPAD), v[ii][q]);
+          }
         }
       }
     }

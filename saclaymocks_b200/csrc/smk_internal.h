@@ -60,7 +60,8 @@ struct MulArgs {
   const float* kc;
   int outer0;      // global index of outer==0 (multi-GPU y offset)
   int fa, fb;      // axes of the factor: 0 = n axis (x), 1 = outer axis (y), 2 = column axis (z)
-  double vscale;   // H0 * dgrowth0 for the velocity products
+  double vscale;   // dgrowth0 of the velocity products (float64 scalar of make_boxes.py:321)
+  float vs_hi, vs_lo;   // the same as an unevaluated float32 pair, filled in by launch_c2c_strided
 };
 
 enum MulMode { MUL_NONE = 0, MUL_TABLE = 1, MUL_ETA = 2, MUL_VEL = 3 };

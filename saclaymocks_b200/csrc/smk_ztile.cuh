@@ -1,0 +1,131 @@
+// Tile transform of the contiguous (z) passes: LINES lines of M complex points in shared memory, layout [line][point].
+// Kept apart from the kernels (smk_boxes.cu) so that tests/fft_stage_host.cpp can run the very same stage code thread by
+// thread on the host (tests/test_fft_stage_cpu.py).
+#pragma once
+#include "smk_fft.cuh"
+
+namespace smk {
+
+// ------------------------------------------------------------------ contiguous (z) pass
+template <int M>
+struct ZTraits {
+  using P = typename PlanFor<M>::type;
+#ifndef SMK_Z_LINES
+#define SMK_Z_LINES 8    // lines per tile of the NZ = 1536 z passes: 8 = four CTAs of 128 threads and 50 KB per SM, whose
+#endif                   // load / transform / store phases interleave better than those of two 16-line CTAs (measured on
+                         // B200, tools/z_lines_check.sh: c2r z 0.787 -> 0.772 ms, r2c z + Philox 1.186 -> 1.147 ms)
+  static constexpr int LINES = (M > 1024) ? 4 : ((M == 768) ? SMK_Z_LINES : 16);
+  static constexpr int NT_ = (M % 3 == 0) ? LINES * M / 48 / 32 * 32 : LINES * M / 32;
+  static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
+  // PERM: two-stage plan R0.R1 with a radix-32 first stage, run without the re-sorting last stage (which would need
+  // all of a thread's butterflies in registers at once).  Natural index k then sits at position (k % R0) R1 + k / R0;
+  // with one float2 of padding after every R1 points, consecutive k are 25 float2 apart for R1 = 24: the permuted
+  // reads of the store / post-processing loops (lane = k) stay free of bank conflicts.
+  static constexpr bool PERM = (P::S == 2 && P::radix(0) >= 32);
+  static constexpr int R0 = P::radix(0), R1 = PERM ? P::radix(1) : 1;
+  static constexpr int LP_ = PERM ? M + M / R1 : M;
+  // pitch: the lanes of a half-warp are LINES lines x 16 / LINES consecutive positions of one stage; with a pitch of
+  // 16 / LINES (mod 16) float2 they fall on 16 different bank pairs (LINES == 16: any odd pitch)
+  static constexpr int pitch(int least) {
+    int lp = least;
+    while (lp % 16 != (16 / LINES) % 16) ++lp;
+    return lp;
+  }
+  static constexpr int LP = (LINES == 16) ? LP_ + 1 - LP_ % 2 : pitch(LP_);
+  __device__ static __forceinline__ int idx(int p) { return PERM ? p + p / R1 : p; }         // padded position
+  __device__ static __forceinline__ int nat(int k) { return PERM ? idx((k % R0) * R1 + k / R0) : k; }   // where output k sits
+};
+
+// Where a non-final stage of the z tile takes its twiddles from (smk_fft.cuh TW_*).  A warp of the z pass holds several
+// lines, so a table load fans out over a few addresses and costs one L1 wavefront each -- 15 loads per radix-16
+// butterfly, about a quarter of the kernel's wavefronts.  Stage 0 loads one twiddle per output and thread and derives
+// those of the thread's other butterflies by a constant rotation; later stages use compile-time constants when a thread
+// can take all the butterflies of one block (NZ = 1536: 16.16.3, the 3 butterflies of each 48-point block).
+#ifndef SMK_Z_TW
+#define SMK_Z_TW 1
+#endif
+template <class P, int STAGE, int LINES, int NT>
+__host__ __device__ constexpr int z_tw_mode() {
+  constexpr int R = P::radix(STAGE), MQ = P::sub(STAGE) / R, NB = P::N / R;
+  constexpr int TPT = (NB * LINES + NT - 1) / NT, JSTEP = NT / LINES;
+  if (!SMK_Z_TW) return TW_TABLE;
+  if (STAGE == 0) return TPT > 1 ? TW_SPLIT : TW_TABLE;
+  return ((NB * LINES) % NT == 0 && TPT == MQ && NB == JSTEP * MQ) ? TW_CONST : TW_TABLE;
+}
+
+// Stage S of the M-point transform of every line of the tile ([line][idx(point)], pitch LP; natural-order input, output
+// k of a line ends at ZTraits<M>::nat(k)).  Reads src and writes dst: the same shared-memory tile on the GPU; the host
+// emulation (tests/fft_stage_host.cpp) hands the re-sorting last stage a copy as src, standing in for its barrier.
+template <int M, bool INV, int S>
+__device__ __forceinline__ void z_tile_stage(const float2* src, float2* dst, const float2* __restrict__ tw) {
+  using ZT = ZTraits<M>;
+  using P = typename ZT::P;
+  constexpr int LINES = ZT::LINES, NT = ZT::NT, LP = ZT::LP;
+  if constexpr (ZT::PERM) {
+    auto ld = [&](int line, int pos, int, int) { return src[line * LP + ZT::idx(pos)]; };
+    auto st = [&](int line, int pos, float2 val) { dst[line * LP + ZT::idx(pos)] = val; };
+    dif_stage<P, S, INV, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 1>(ld, st, tw, 2);
+  } else {
+    auto ld = [&](int line, int pos, int, int) { return src[line * LP + pos]; };
+    auto st = [&](int line, int pos, float2 val) { dst[line * LP + pos] = val; };
+    if constexpr (S == P::S - 1) {
+      dif_stage<P, S, INV, LINES, NT, OUT_RESORT>(ld, st, tw, 2);
+    } else {
+      // unpadded tile: only the first stage can do without per-task table loads (TW_CONST needs the padded layout)
+      constexpr int TW = (S == 0) ? z_tw_mode<P, 0, LINES, NT>() : TW_TABLE;
+      dif_stage<P, S, INV, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, 0, TW>(ld, st, tw, 2);
+    }
+  }
+}
+
+// all stages, a barrier after each
+template <int M, bool INV, int S = 0>
+__device__ __forceinline__ void z_tile_fft(float2* sm, const float2* __restrict__ tw) {
+  if constexpr (S < ZTraits<M>::P::S) {
+    z_tile_stage<M, INV, S>(sm, sm, tw);
+    __syncthreads();
+    z_tile_fft<M, INV, S + 1>(sm, tw);
+  }
+}
+
+// Inverse z pass with the last DIF stage fused into the store (plans of >= 2 stages): the last stage has no twiddles and
+// its butterfly b = pos(n0) / RL produces the natural outputs n0 + q M/RL, so a warp whose lanes take CONSECUTIVE n0
+// runs it straight from shared memory into coalesced global stores -- the re-sort (one shared-memory write + read of
+// the tile) and the separate store loop's read disappear (8 -> 6 passes over the tile in shared memory; the kernel is
+// bound by that pipe).  Consecutive n0 read positions M/R0 apart: one float2 of padding after every M/R0 positions
+// makes that stride odd in units of 8 bytes, i.e. conflict free for the 16 lanes of a half-warp.
+template <int M>
+struct C2RTraits {
+  using ZT = ZTraits<M>;
+  using P = typename ZT::P;
+  static constexpr int R0 = P::radix(0), RL = P::radix(P::S - 1), BLK = M / R0, NB = M / RL;
+  static constexpr bool FUSE = (P::S >= 2) && !ZT::PERM && (BLK % 2 == 0) && (BLK % RL == 0) && (M >= 32);
+  static constexpr int LP_ = M + R0;
+  static constexpr int LP = FUSE ? (ZT::LINES == 16 ? (LP_ + 1 - LP_ % 2) : ZT::pitch(LP_)) : ZT::LP;
+  __device__ static __forceinline__ int idx(int p) { return FUSE ? p + p / BLK : ZT::idx(p); }
+};
+
+// stages [S0, S1) in place through the padded index, a barrier after each
+template <class CT, int S0, int S1, int LINES, int NT, int LP>
+__device__ __forceinline__ void c2r_stages(float2* sm, const float2* __restrict__ tw) {
+  if constexpr (S0 < S1) {
+    auto ld = [&](int line, int ppos, int, int) { return sm[line * LP + ppos]; };          // padded positions
+    auto st = [&](int line, int ppos, float2 val) { sm[line * LP + ppos] = val; };
+    dif_stage<typename CT::P, S0, true, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, CT::BLK,
+              z_tw_mode<typename CT::P, S0, LINES, NT>()>(ld, st, tw, 2);
+    __syncthreads();
+    c2r_stages<CT, S0 + 1, S1, LINES, NT, LP>(sm, tw);
+  }
+}
+
+// last (twiddle-free) stage of the fused inverse z pass, run per natural output index n0 < NB straight out of shared
+// memory: v[q] = output n0 + q NB of the line
+template <class CT>
+__device__ __forceinline__ void c2r_last_butterfly(const float2* row, int n0, float2 (&v)[CT::RL]) {
+  const int pb = CT::P::pos(n0);
+#pragma unroll
+  for (int t = 0; t < CT::RL; ++t) v[t] = row[CT::idx(pb + t)];
+  Butterfly<CT::RL, true>::run(v);
+}
+
+}  // namespace smk

@@ -1,0 +1,187 @@
+// Runs the inverse z pass's in-place DIF stages (smk_ztile.cuh: c2r_stages + c2r_last_butterfly, i.e. the code
+// c2r_z_kernel executes between its load and its store) thread by thread on the host and compares every line with a
+// float64 inverse DFT.  Checks the index logic of the padded layout and of the three twiddle sources (table, split,
+// compile-time constants) without a GPU.  Built and run by tests/test_fft_stage_cpu.py with g++ -Itests/host_stub.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "smk_ztile.cuh"
+
+using namespace smk;
+
+template <class CT, int S, int SEND, int LINES, int NT, int LP>
+static void run_stages(float2* sm, const float2* tw) {
+  if constexpr (S < SEND) {
+    for (unsigned tid = 0; tid < (unsigned)NT; ++tid) {   // a barrier separates the stages on the GPU
+      threadIdx.x = tid;
+      c2r_stages<CT, S, S + 1, LINES, NT, LP>(sm, tw);
+    }
+    run_stages<CT, S + 1, SEND, LINES, NT, LP>(sm, tw);
+  }
+}
+
+// Shared-memory wavefronts of one stage's loads: the k-th 8-byte load of the 32 threads of a warp is one request; each
+// half-warp needs as many passes as the most loaded of the 16 bank pairs (distinct addresses only).  Returns the
+// average over the stage's requests (2.0 = conflict free).  Same dif_stage instantiation as c2r_stages.
+template <class CT, int S, int LINES, int NT, int LP>
+static double stage_wavefronts(float2* sm, const float2* tw, long long* tw_requests, long long* tw_wavefronts) {
+  std::vector<std::vector<int>> log(NT);
+  std::vector<std::vector<const void*>> glog(NT);
+  for (unsigned tid = 0; tid < (unsigned)NT; ++tid) {
+    threadIdx.x = tid;
+    smk_host_ldg_log = &glog[tid];
+    auto ld = [&](int line, int ppos, int, int) { log[tid].push_back(line * LP + ppos); return sm[line * LP + ppos]; };
+    auto st = [&](int, int, float2) {};
+    dif_stage<typename CT::P, S, true, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, CT::BLK,
+              z_tw_mode<typename CT::P, S, LINES, NT>()>(ld, st, tw, 2);
+  }
+  smk_host_ldg_log = nullptr;
+  // twiddle loads: one L1 wavefront per distinct 128-byte line of a warp's request
+  long long greq = 0, glines = 0;
+  for (int w = 0; w < NT / 32; ++w)
+    for (size_t k = 0; k < glog[w * 32].size(); ++k, ++greq) {
+      std::vector<uintptr_t> lines;
+      for (int l = 0; l < 32; ++l) {
+        if (k >= glog[w * 32 + l].size()) continue;
+        const uintptr_t a = ((uintptr_t)glog[w * 32 + l][k] - (uintptr_t)tw) / 128;
+        bool dup = false;
+        for (uintptr_t x : lines) dup |= (x == a);
+        if (!dup) lines.push_back(a);
+      }
+      glines += (long long)lines.size();
+    }
+  *tw_requests = greq;
+  *tw_wavefronts = glines;
+  long long req = 0, wf = 0;
+  for (int w = 0; w < NT / 32; ++w)
+    for (size_t k = 0; k < log[w * 32].size(); ++k, ++req)
+      for (int h = 0; h < 2; ++h) {
+        int cnt[16] = {0}, seen[16][16];
+        for (int l = 0; l < 16; ++l) {
+          const std::vector<int>& v = log[w * 32 + h * 16 + l];
+          if (k >= v.size()) continue;
+          const int a = v[k], b = a & 15;
+          bool dup = false;
+          for (int i = 0; i < cnt[b]; ++i) dup |= (seen[b][i] == a);
+          if (!dup) seen[b][cnt[b]++] = a;
+        }
+        int mx = 0;
+        for (int b = 0; b < 16; ++b) mx = cnt[b] > mx ? cnt[b] : mx;
+        wf += mx;
+      }
+  return req ? (double)wf / req : 0.;
+}
+
+template <int M>
+static int check() {
+  using CT = C2RTraits<M>;
+  using ZT = ZTraits<M>;
+  using P = typename CT::P;
+  if constexpr (!CT::FUSE) {
+    printf("M=%d not fused: skipped\n", M);
+    return 0;
+  } else {
+    constexpr int LINES = ZT::LINES, NT = ZT::NT, LP = CT::LP, RL = CT::RL, NB = CT::NB;
+    std::vector<float2> sm((size_t)LINES * LP, make_float2(0.f, 0.f)), tw(2 * M);
+    for (int k = 0; k < 2 * M; ++k) tw[k] = make_float2((float)cos(M_PI * k / M), (float)-sin(M_PI * k / M));   // W_2M
+    std::vector<double> zr(LINES * M), zi(LINES * M);
+    srand(1234 + M);
+    for (int l = 0; l < LINES; ++l)
+      for (int n = 0; n < M; ++n) {
+        zr[l * M + n] = rand() / (double)RAND_MAX - 0.5;
+        zi[l * M + n] = rand() / (double)RAND_MAX - 0.5;
+        sm[(size_t)l * LP + CT::idx(n)] = make_float2((float)zr[l * M + n], (float)zi[l * M + n]);
+      }
+    long long treq[2] = {0, 0}, twf[2] = {0, 0};
+    const double wf0 = stage_wavefronts<CT, 0, LINES, NT, LP>(sm.data(), tw.data(), &treq[0], &twf[0]);
+    double wf1 = 0.;
+    if constexpr (P::S > 2) wf1 = stage_wavefronts<CT, 1, LINES, NT, LP>(sm.data(), tw.data(), &treq[1], &twf[1]);
+    run_stages<CT, 0, P::S - 1, LINES, NT, LP>(sm.data(), tw.data());
+    double worst = 0., scale = 0.;
+    for (int l = 0; l < LINES; ++l) {
+      std::vector<float2> out(M);
+      for (int n0 = 0; n0 < NB; ++n0) {
+        float2 v[RL];
+        c2r_last_butterfly<CT>(sm.data() + (size_t)l * LP, n0, v);
+        for (int q = 0; q < RL; ++q) out[n0 + q * NB] = v[q];
+      }
+      for (int n = 0; n < M; ++n) {
+        double re = 0., im = 0.;
+        for (int k = 0; k < M; ++k) {
+          const double a = 2. * M_PI * (double)((long long)k * n % M) / M, c = cos(a), s = sin(a);
+          re += zr[l * M + k] * c - zi[l * M + k] * s;
+          im += zr[l * M + k] * s + zi[l * M + k] * c;
+        }
+        worst = fmax(worst, fmax(fabs(out[n].x - re), fabs(out[n].y - im)));
+        scale = fmax(scale, fmax(fabs(re), fabs(im)));
+      }
+    }
+    const double rel = worst / scale;
+    printf("M=%d lines=%d threads=%d tw_modes=%d,%d lds_wavefronts_per_request=%.2f,%.2f "
+           "twiddle_loads_per_tile=%lld,%lld twiddle_wavefronts_per_tile=%lld,%lld (tile data: %d) max_err/max=%.3g %s\n",
+           M, LINES, NT, z_tw_mode<P, 0, LINES, NT>(), P::S > 2 ? z_tw_mode<P, 1, LINES, NT>() : -1, wf0, wf1, treq[0],
+           treq[1], twf[0], twf[1], LINES * M * 8 / 128, rel, rel < 2e-6 ? "ok" : "FAIL");
+    return rel < 2e-6 ? 0 : 1;
+  }
+}
+
+// z_tile_fft (forward r2c tiles, and the inverse tiles that are not fused): every stage for all threads, the stage's
+// input taken from a copy of the tile (what the barrier inside the re-sorting last stage guarantees on the GPU)
+template <int M, bool INV, int S>
+static void run_tile_stages(std::vector<float2>& sm, const float2* tw) {
+  using ZT = ZTraits<M>;
+  if constexpr (S < ZT::P::S) {
+    const std::vector<float2> src = sm;
+    for (unsigned tid = 0; tid < (unsigned)ZT::NT; ++tid) {
+      threadIdx.x = tid;
+      z_tile_stage<M, INV, S>(src.data(), sm.data(), tw);
+    }
+    run_tile_stages<M, INV, S + 1>(sm, tw);
+  }
+}
+
+template <int M, bool INV>
+static int check_tile() {
+  using ZT = ZTraits<M>;
+  constexpr int LINES = ZT::LINES, LP = ZT::LP;
+  std::vector<float2> sm((size_t)LINES * LP, make_float2(0.f, 0.f)), tw(2 * M);
+  for (int k = 0; k < 2 * M; ++k) tw[k] = make_float2((float)cos(M_PI * k / M), (float)-sin(M_PI * k / M));   // W_2M
+  std::vector<double> zr(LINES * M), zi(LINES * M);
+  srand(99 + M);
+  for (int l = 0; l < LINES; ++l)
+    for (int n = 0; n < M; ++n) {
+      zr[l * M + n] = rand() / (double)RAND_MAX - 0.5;
+      zi[l * M + n] = rand() / (double)RAND_MAX - 0.5;
+      sm[(size_t)l * LP + ZT::idx(n)] = make_float2((float)zr[l * M + n], (float)zi[l * M + n]);
+    }
+  run_tile_stages<M, INV, 0>(sm, tw.data());
+  double worst = 0., scale = 0.;
+  for (int l = 0; l < LINES; ++l)
+    for (int k = 0; k < M; ++k) {
+      double re = 0., im = 0.;
+      for (int n = 0; n < M; ++n) {
+        const double a = (INV ? 2. : -2.) * M_PI * (double)((long long)k * n % M) / M, c = cos(a), sn = sin(a);
+        re += zr[l * M + n] * c - zi[l * M + n] * sn;
+        im += zr[l * M + n] * sn + zi[l * M + n] * c;
+      }
+      const float2 got = sm[(size_t)l * LP + ZT::nat(k)];
+      worst = fmax(worst, fmax(fabs(got.x - re), fabs(got.y - im)));
+      scale = fmax(scale, fmax(fabs(re), fabs(im)));
+    }
+  const double rel = worst / scale;
+  printf("tile M=%d %s lines=%d threads=%d perm=%d max_err/max=%.3g %s\n", M, INV ? "inverse" : "forward", LINES, ZT::NT,
+         (int)ZT::PERM, rel, rel < 2e-6 ? "ok" : "FAIL");
+  return rel < 2e-6 ? 0 : 1;
+}
+
+int main() {
+  int bad = 0;
+  // every tile shape the C ABI dispatches (NZ/2): forward tiles, the inverse tiles that are not fused, the fused inverse
+  bad += check_tile<4, false>() + check_tile<8, false>() + check_tile<12, false>() + check_tile<16, false>();
+  bad += check_tile<32, false>() + check_tile<48, false>() + check_tile<64, false>() + check_tile<128, false>();
+  bad += check_tile<256, false>() + check_tile<512, false>() + check_tile<768, false>();
+  bad += check_tile<4, true>() + check_tile<8, true>() + check_tile<12, true>() + check_tile<16, true>();
+  bad += check_tile<64, true>() + check_tile<512, true>();
+  bad += check<32>() + check<48>() + check<128>() + check<256>() + check<384>() + check<768>() + check<2048>();
+  return bad;
+}
