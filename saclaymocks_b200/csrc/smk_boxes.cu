@@ -327,9 +327,9 @@ struct R2CParams {
 
 template <int M, bool PHILOX>
 // (as for c2r_z_kernel: four 8-line CTAs per SM at NZ = 1536 need 128 registers or fewer)
-__global__ void __launch_bounds__(ZTraits<M>::NT, (M == 768) ? 32 / ZTraits<M>::LINES : 1) r2c_z_kernel(R2CParams p) {
-  using ZT = ZTraits<M>;
-  constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = ZTraits<M>::LP;
+__global__ void __launch_bounds__(ZFwd<M>::NT, (M == 768) ? 32 / ZFwd<M>::LINES : 1) r2c_z_kernel(R2CParams p) {
+  using ZT = ZFwd<M>;
+  constexpr int LINES = ZFwd<M>::LINES, NT = ZFwd<M>::NT, LP = ZFwd<M>::LP;
   extern __shared__ float2 sm[];   // [LINES][LP]
   const long long line0 = (long long)blockIdx.x * LINES;
   // ---- load (or draw) the real lines as M float2 each
@@ -393,10 +393,10 @@ struct C2RParams {
 
 template <int M>
 // two CTAs of (M >= 512: 98 KB) share an SM: the register allocation has to leave room for both
-__global__ void __launch_bounds__(ZTraits<M>::NT, (M >= 512) ? 32 / ZTraits<M>::LINES : 1) c2r_z_kernel(C2RParams p) {
-  using ZT = ZTraits<M>;
+__global__ void __launch_bounds__(ZInv<M>::NT, (M >= 512) ? 32 / ZInv<M>::LINES : 1) c2r_z_kernel(C2RParams p) {
+  using ZT = ZInv<M>;
   using CT = C2RTraits<M>;
-  constexpr int LINES = ZTraits<M>::LINES, NT = ZTraits<M>::NT, LP = CT::LP;
+  constexpr int LINES = ZInv<M>::LINES, NT = ZInv<M>::NT, LP = CT::LP;
   extern __shared__ float2 sm[];
   __shared__ double red[2][NT / 32];
   const long long line0 = (long long)blockIdx.x * LINES;
@@ -524,16 +524,16 @@ bool z_size_supported(int nz) {
 
 template <int M>
 static int launch_r2c_t(const R2CParams& p, bool philox, cudaStream_t st) {
-  size_t smem = (size_t)ZTraits<M>::LINES * ZTraits<M>::LP * sizeof(float2);
-  unsigned grid = (unsigned)((p.nlines + ZTraits<M>::LINES - 1) / ZTraits<M>::LINES);
+  size_t smem = (size_t)ZFwd<M>::LINES * ZFwd<M>::LP * sizeof(float2);
+  unsigned grid = (unsigned)((p.nlines + ZFwd<M>::LINES - 1) / ZFwd<M>::LINES);
   if (philox) {
     auto kern = r2c_z_kernel<M, true>;
     if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, ZTraits<M>::NT, smem, st>>>(p);
+    kern<<<grid, ZFwd<M>::NT, smem, st>>>(p);
   } else {
     auto kern = r2c_z_kernel<M, false>;
     if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, ZTraits<M>::NT, smem, st>>>(p);
+    kern<<<grid, ZFwd<M>::NT, smem, st>>>(p);
   }
   SMK_CUDA_OK(cudaGetLastError());
   return SMK_OK;
@@ -558,11 +558,11 @@ int launch_r2c_z(int NZ, const float* in, float2* out, long long nlines, int pit
 // more than the overlap gains.  profiles/README.md.)
 template <int M>
 static int launch_c2r_t(const C2RParams& p, cudaStream_t st) {
-  size_t smem = (size_t)ZTraits<M>::LINES * C2RTraits<M>::LP * sizeof(float2);
-  unsigned grid = (unsigned)((p.nlines + ZTraits<M>::LINES - 1) / ZTraits<M>::LINES);
+  size_t smem = (size_t)ZInv<M>::LINES * C2RTraits<M>::LP * sizeof(float2);
+  unsigned grid = (unsigned)((p.nlines + ZInv<M>::LINES - 1) / ZInv<M>::LINES);
   auto kern = c2r_z_kernel<M>;
   if (smem > 48 * 1024) SMK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, ZTraits<M>::NT, smem, st>>>(p);
+  kern<<<grid, ZInv<M>::NT, smem, st>>>(p);
   SMK_CUDA_OK(cudaGetLastError());
   return SMK_OK;
 }

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "smk_internal.h"
+#include "smk_ztile.cuh"
 
 namespace smk {
 static thread_local std::string g_err;
@@ -78,6 +79,16 @@ static int make_twiddles(int n, float2** dptr, size_t* bytes) {
   SMK_CUDA_OK(cudaMalloc(dptr, n * sizeof(float2)));
   SMK_CUDA_OK(cudaMemcpy(*dptr, h.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
   *bytes += n * sizeof(float2);
+  return SMK_OK;
+}
+
+// W_NZ plus the z passes' compact first-stage table (smk_ztile.cuh)
+static int make_z_twiddles(int nz, float2** dptr, size_t* bytes) {
+  std::vector<float2> h;
+  z_twiddle_table(nz, h);
+  SMK_CUDA_OK(cudaMalloc(dptr, h.size() * sizeof(float2)));
+  SMK_CUDA_OK(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  *bytes += h.size() * sizeof(float2);
   return SMK_OK;
 }
 
@@ -230,7 +241,7 @@ static int ctx_allocate(smk_ctx* c) {
   int rc;
   if ((rc = make_twiddles(c->nx, &c->tw_x, &c->bytes))) return rc;
   if ((rc = make_twiddles(c->ny, &c->tw_y, &c->bytes))) return rc;
-  if ((rc = make_twiddles(c->nz, &c->tw_z, &c->bytes))) return rc;
+  if ((rc = make_z_twiddles(c->nz, &c->tw_z, &c->bytes))) return rc;
   if ((rc = make_ktable(c->nx, false, c->dcell, &c->kx, &c->bytes))) return rc;
   if ((rc = make_ktable(c->ny, false, c->dcell, &c->ky, &c->bytes))) return rc;
   if ((rc = make_ktable(c->nz, true, c->dcell, &c->kz, &c->bytes))) return rc;

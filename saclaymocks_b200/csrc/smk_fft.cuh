@@ -413,14 +413,16 @@ struct NoPre {
 // shared-memory-bound z passes costs as much as the data:
 //   TW_TABLE  one table load per output and task (the general case);
 //   TW_SPLIT  (stage 0, where o = j0 + i JSTEP for the thread's task i) one load W^(q j0) per output, shared by the
-//             thread's tasks: task i multiplies it by the compile-time constant W^(q i JSTEP);
+//             thread's tasks: task i multiplies it by the compile-time constant W^(q i JSTEP).  With SPLIT_ROW > 0 the
+//             load comes from a compact table T[q][j0] = W_N^(q j0) (rows of SPLIT_ROW entries, stored behind W_L at
+//             tw + L): the lanes of a request then read neighbouring entries, one wavefront instead of one per j0;
 //   TW_CONST  the thread takes the MQ butterflies of ONE block b = j0 (o = i is a compile-time value): no loads at
 //             all.  Needs MQ tasks per thread; tasks of neighbouring threads are then a whole sub-transform apart, so
 //             the tile needs the padded layout to stay free of bank conflicts.
 enum { TW_TABLE = 0, TW_SPLIT = 1, TW_CONST = 2 };
 
 template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store, class Pre = NoPre,
-          int BATCH = 0, int PADBLK = 0, int TW = TW_TABLE>
+          int BATCH = 0, int PADBLK = 0, int TW = TW_TABLE, int SPLIT_ROW = 0>
 __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __restrict__ tw, int twmul,
                                           Pre pre = Pre()) {
   constexpr int R = P::radix(STAGE);
@@ -444,6 +446,7 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
   constexpr bool EVEN = (NTASK % NT == 0);
   constexpr int JSTEP = NT / LINES;
   static_assert(TW != TW_SPLIT || (STAGE == 0 && !LAST), "split twiddles: first stage of a multi-stage plan");
+  static_assert(SPLIT_ROW == 0 || NT / LINES <= SPLIT_ROW, "compact twiddle table: one row entry per butterfly slot j0");
   static_assert(TW != TW_CONST || (!LAST && EVEN && TB == TPT && TPT == MQ && NB == JSTEP * MQ),
                 "constant twiddles: one block of MQ butterflies per thread");
   // a thread always works on the same line: task = threadIdx.x + i*NT  =>  line = threadIdx.x % LINES
@@ -484,7 +487,7 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
       const int oc = j0 * twmul;                    // W_N^(q j0) = W_L[q j0 twmul]
 #pragma unroll
       for (int q = 1; q < R; ++q) {
-        float2 w = __ldg(tw + q * oc);
+        float2 w = SPLIT_ROW > 0 ? __ldg(tw + P::N * twmul + q * SPLIT_ROW + j0) : __ldg(tw + q * oc);
         if (INV) w.y = -w.y;
 #pragma unroll
         for (int ii = 0; ii < TB; ++ii) {

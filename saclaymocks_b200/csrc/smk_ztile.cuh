@@ -2,19 +2,28 @@
 // Kept apart from the kernels (smk_boxes.cu) so that tests/fft_stage_host.cpp can run the very same stage code thread by
 // thread on the host (tests/test_fft_stage_cpu.py).
 #pragma once
+#include <math.h>
+#include <vector>
 #include "smk_fft.cuh"
 
 namespace smk {
 
 // ------------------------------------------------------------------ contiguous (z) pass
-template <int M>
+// INVERSE selects the tile height of the NZ = 1536 passes, which differs between the two directions.
+template <int M, bool INVERSE = false>
 struct ZTraits {
   using P = typename PlanFor<M>::type;
+  // Lines per tile of the NZ = 1536 z passes, measured on B200 (tools/ab_check.sh): smaller tiles mean more, smaller CTAs
+  // per SM (8 lines: four of 128 threads and 50 KB; 4 lines: eight of 64 threads), whose load / transform / store phases
+  // interleave better.  16 -> 8 lines: c2r z 0.787 -> 0.772 ms, r2c z + Philox 1.186 -> 1.147 ms; 8 -> 4 lines (after the
+  // twiddle loads had gone): c2r z 0.690 -> 0.674 ms but r2c z 1.139 -> 1.172 ms, hence 4 for the inverse pass only.
 #ifndef SMK_Z_LINES
-#define SMK_Z_LINES 8    // lines per tile of the NZ = 1536 z passes: 8 = four CTAs of 128 threads and 50 KB per SM, whose
-#endif                   // load / transform / store phases interleave better than those of two 16-line CTAs (measured on
-                         // B200, tools/z_lines_check.sh: c2r z 0.787 -> 0.772 ms, r2c z + Philox 1.186 -> 1.147 ms)
-  static constexpr int LINES = (M > 1024) ? 4 : ((M == 768) ? SMK_Z_LINES : 16);
+#define SMK_Z_LINES 8
+#endif
+#ifndef SMK_Z_LINES_C2R
+#define SMK_Z_LINES_C2R 4
+#endif
+  static constexpr int LINES = (M > 1024) ? 4 : ((M == 768) ? (INVERSE ? SMK_Z_LINES_C2R : SMK_Z_LINES) : 16);
   static constexpr int NT_ = (M % 3 == 0) ? LINES * M / 48 / 32 * 32 : LINES * M / 32;
   static constexpr int NT = NT_ < 64 ? 64 : (NT_ > 512 ? 512 : NT_);
   // PERM: two-stage plan R0.R1 with a radix-32 first stage, run without the re-sorting last stage (which would need
@@ -36,14 +45,34 @@ struct ZTraits {
   __device__ static __forceinline__ int nat(int k) { return PERM ? idx((k % R0) * R1 + k / R0) : k; }   // where output k sits
 };
 
+template <int M> using ZFwd = ZTraits<M, false>;   // tiles of the forward (r2c) pass
+template <int M> using ZInv = ZTraits<M, true>;    // tiles of the inverse (c2r) pass
+
 // Where a non-final stage of the z tile takes its twiddles from (smk_fft.cuh TW_*).  A warp of the z pass holds several
 // lines, so a table load fans out over a few addresses and costs one L1 wavefront each -- 15 loads per radix-16
 // butterfly, about a quarter of the kernel's wavefronts.  Stage 0 loads one twiddle per output and thread and derives
 // those of the thread's other butterflies by a constant rotation; later stages use compile-time constants when a thread
 // can take all the butterflies of one block (NZ = 1536: 16.16.3, the 3 butterflies of each 48-point block).
 #ifndef SMK_Z_TW
-#define SMK_Z_TW 1
+#define SMK_Z_TW 2   // 0: table loads everywhere, 1: split / constant twiddles, 2: and stage 0 reads the compact table
 #endif
+// The z passes' twiddle table: W_NZ[k] = exp(-2 pi i k / NZ), k < NZ, followed by the compact first-stage table
+// T[q][j] = W_M^(q j) (M = NZ / 2, q < Z_SPLIT_ROWS, j < Z_SPLIT_ROW) read by TW_SPLIT.
+constexpr int Z_SPLIT_ROW = 64, Z_SPLIT_ROWS = 32;
+inline void z_twiddle_table(int nz, std::vector<float2>& h) {
+  const double PI = 3.14159265358979323846;
+  h.resize((size_t)nz + Z_SPLIT_ROWS * Z_SPLIT_ROW);
+  for (int k = 0; k < nz; ++k) {
+    const double a = -2.0 * PI * (double)k / (double)nz;
+    h[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  const int m = nz / 2;
+  for (int q = 0; q < Z_SPLIT_ROWS; ++q)
+    for (int j = 0; j < Z_SPLIT_ROW; ++j) {
+      const double a = -2.0 * PI * (double)((long long)q * j % m) / (double)m;
+      h[(size_t)nz + q * Z_SPLIT_ROW + j] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
 template <class P, int STAGE, int LINES, int NT>
 __host__ __device__ constexpr int z_tw_mode() {
   constexpr int R = P::radix(STAGE), MQ = P::sub(STAGE) / R, NB = P::N / R;
@@ -54,11 +83,11 @@ __host__ __device__ constexpr int z_tw_mode() {
 }
 
 // Stage S of the M-point transform of every line of the tile ([line][idx(point)], pitch LP; natural-order input, output
-// k of a line ends at ZTraits<M>::nat(k)).  Reads src and writes dst: the same shared-memory tile on the GPU; the host
+// k of a line ends at ZTraits<M, INV>::nat(k)).  Reads src and writes dst: the same shared-memory tile on the GPU; the host
 // emulation (tests/fft_stage_host.cpp) hands the re-sorting last stage a copy as src, standing in for its barrier.
 template <int M, bool INV, int S>
 __device__ __forceinline__ void z_tile_stage(const float2* src, float2* dst, const float2* __restrict__ tw) {
-  using ZT = ZTraits<M>;
+  using ZT = ZTraits<M, INV>;
   using P = typename ZT::P;
   constexpr int LINES = ZT::LINES, NT = ZT::NT, LP = ZT::LP;
   if constexpr (ZT::PERM) {
@@ -73,7 +102,8 @@ __device__ __forceinline__ void z_tile_stage(const float2* src, float2* dst, con
     } else {
       // unpadded tile: only the first stage can do without per-task table loads (TW_CONST needs the padded layout)
       constexpr int TW = (S == 0) ? z_tw_mode<P, 0, LINES, NT>() : TW_TABLE;
-      dif_stage<P, S, INV, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, 0, TW>(ld, st, tw, 2);
+      dif_stage<P, S, INV, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, 0, TW,
+                (SMK_Z_TW >= 2) ? Z_SPLIT_ROW : 0>(ld, st, tw, 2);
     }
   }
 }
@@ -81,7 +111,7 @@ __device__ __forceinline__ void z_tile_stage(const float2* src, float2* dst, con
 // all stages, a barrier after each
 template <int M, bool INV, int S = 0>
 __device__ __forceinline__ void z_tile_fft(float2* sm, const float2* __restrict__ tw) {
-  if constexpr (S < ZTraits<M>::P::S) {
+  if constexpr (S < PlanFor<M>::type::S) {
     z_tile_stage<M, INV, S>(sm, sm, tw);
     __syncthreads();
     z_tile_fft<M, INV, S + 1>(sm, tw);
@@ -96,7 +126,7 @@ __device__ __forceinline__ void z_tile_fft(float2* sm, const float2* __restrict_
 // makes that stride odd in units of 8 bytes, i.e. conflict free for the 16 lanes of a half-warp.
 template <int M>
 struct C2RTraits {
-  using ZT = ZTraits<M>;
+  using ZT = ZTraits<M, true>;
   using P = typename ZT::P;
   static constexpr int R0 = P::radix(0), RL = P::radix(P::S - 1), BLK = M / R0, NB = M / RL;
   static constexpr bool FUSE = (P::S >= 2) && !ZT::PERM && (BLK % 2 == 0) && (BLK % RL == 0) && (M >= 32);
@@ -112,7 +142,7 @@ __device__ __forceinline__ void c2r_stages(float2* sm, const float2* __restrict_
     auto ld = [&](int line, int ppos, int, int) { return sm[line * LP + ppos]; };          // padded positions
     auto st = [&](int line, int ppos, float2 val) { sm[line * LP + ppos] = val; };
     dif_stage<typename CT::P, S0, true, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, CT::BLK,
-              z_tw_mode<typename CT::P, S0, LINES, NT>()>(ld, st, tw, 2);
+              z_tw_mode<typename CT::P, S0, LINES, NT>(), (SMK_Z_TW >= 2) ? Z_SPLIT_ROW : 0>(ld, st, tw, 2);
     __syncthreads();
     c2r_stages<CT, S0 + 1, S1, LINES, NT, LP>(sm, tw);
   }

@@ -33,7 +33,7 @@ static double stage_wavefronts(float2* sm, const float2* tw, long long* tw_reque
     auto ld = [&](int line, int ppos, int, int) { log[tid].push_back(line * LP + ppos); return sm[line * LP + ppos]; };
     auto st = [&](int, int, float2) {};
     dif_stage<typename CT::P, S, true, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, CT::BLK,
-              z_tw_mode<typename CT::P, S, LINES, NT>()>(ld, st, tw, 2);
+              z_tw_mode<typename CT::P, S, LINES, NT>(), (SMK_Z_TW >= 2) ? Z_SPLIT_ROW : 0>(ld, st, tw, 2);
   }
   smk_host_ldg_log = nullptr;
   // twiddle loads: one L1 wavefront per distinct 128-byte line of a warp's request
@@ -75,15 +75,15 @@ static double stage_wavefronts(float2* sm, const float2* tw, long long* tw_reque
 template <int M>
 static int check() {
   using CT = C2RTraits<M>;
-  using ZT = ZTraits<M>;
+  using ZT = typename CT::ZT;
   using P = typename CT::P;
   if constexpr (!CT::FUSE) {
     printf("M=%d not fused: skipped\n", M);
     return 0;
   } else {
     constexpr int LINES = ZT::LINES, NT = ZT::NT, LP = CT::LP, RL = CT::RL, NB = CT::NB;
-    std::vector<float2> sm((size_t)LINES * LP, make_float2(0.f, 0.f)), tw(2 * M);
-    for (int k = 0; k < 2 * M; ++k) tw[k] = make_float2((float)cos(M_PI * k / M), (float)-sin(M_PI * k / M));   // W_2M
+    std::vector<float2> sm((size_t)LINES * LP, make_float2(0.f, 0.f)), tw;
+    z_twiddle_table(2 * M, tw);   // what smk_capi.cu uploads for NZ = 2 M
     std::vector<double> zr(LINES * M), zi(LINES * M);
     srand(1234 + M);
     for (int l = 0; l < LINES; ++l)
@@ -129,7 +129,7 @@ static int check() {
 // input taken from a copy of the tile (what the barrier inside the re-sorting last stage guarantees on the GPU)
 template <int M, bool INV, int S>
 static void run_tile_stages(std::vector<float2>& sm, const float2* tw) {
-  using ZT = ZTraits<M>;
+  using ZT = ZTraits<M, INV>;
   if constexpr (S < ZT::P::S) {
     const std::vector<float2> src = sm;
     for (unsigned tid = 0; tid < (unsigned)ZT::NT; ++tid) {
@@ -142,10 +142,10 @@ static void run_tile_stages(std::vector<float2>& sm, const float2* tw) {
 
 template <int M, bool INV>
 static int check_tile() {
-  using ZT = ZTraits<M>;
+  using ZT = ZTraits<M, INV>;
   constexpr int LINES = ZT::LINES, LP = ZT::LP;
-  std::vector<float2> sm((size_t)LINES * LP, make_float2(0.f, 0.f)), tw(2 * M);
-  for (int k = 0; k < 2 * M; ++k) tw[k] = make_float2((float)cos(M_PI * k / M), (float)-sin(M_PI * k / M));   // W_2M
+  std::vector<float2> sm((size_t)LINES * LP, make_float2(0.f, 0.f)), tw;
+  z_twiddle_table(2 * M, tw);   // what smk_capi.cu uploads for NZ = 2 M
   std::vector<double> zr(LINES * M), zi(LINES * M);
   srand(99 + M);
   for (int l = 0; l < LINES; ++l)

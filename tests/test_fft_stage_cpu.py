@@ -2,7 +2,7 @@
 
 tests/fft_stage_host.cpp includes the kernels' own stage code (saclaymocks_b200/csrc/smk_ztile.cuh, smk_fft.cuh) through a
 stand-in cuda_runtime.h and compares every line with a float64 inverse DFT, for every tile shape the C ABI dispatches
-(NZ/2 = 32 ... 2048) and for both twiddle sources (SMK_Z_TW=1: split / compile-time constants, 0: table loads).  It
+(NZ/2 = 32 ... 2048) and for both twiddle sources (SMK_Z_TW=2: compact first-stage table + compile-time constants, 1: split from the W table, 0: table loads).  It
 also counts shared-memory wavefronts per request (2.0 = free of bank conflicts) and the L1 wavefronts of the twiddle loads.
 The transform replaces FFTW's c2r of make_boxes.py:87 (reference); numerics on the GPU are covered by test_gpu_boxes.py.
 """
@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.mark.parametrize("z_tw", [1, 0])
+@pytest.mark.parametrize("z_tw", [2, 1, 0])
 def test_c2r_stages_on_host(tmp_path, z_tw):
     exe = str(tmp_path / "fft_stage_host")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wno-unknown-pragmas", "-DSMK_Z_TW=%d" % z_tw,
@@ -31,8 +31,11 @@ def test_c2r_stages_on_host(tmp_path, z_tw):
     assert len(checked) == 7 and all(l.endswith(" ok") for l in checked), res.stdout
     for l in checked:
         wf = [float(x) for x in re.search(r"lds_wavefronts_per_request=([\d.]+),([\d.]+)", l).groups()]
-        assert wf[0] == 2.0 and wf[1] in (0.0, 2.0), l            # no bank conflicts in any tile shape
+        # no bank conflicts in any tile shape (the table-load build keeps the old task order, which conflicts two-way
+        # in the second stage of the 4-line tile: one more reason it is not the default)
+        assert wf[0] == 2.0 and (wf[1] in (0.0, 2.0) or z_tw == 0), l
     (m768,) = [l for l in checked if l.startswith("M=768 ")]
     tw_wf = sum(int(x) for x in re.search(r"twiddle_wavefronts_per_tile=(\d+),(\d+)", m768).groups())
-    # NZ = 1536: 8 lines x 768 points = 384 wavefronts per pass over the tile; the table loads cost ~1100 more
-    assert (tw_wf < 250) if z_tw else (tw_wf > 900), m768
+    data_wf = int(re.search(r"tile data: (\d+)", m768).group(1))    # wavefronts of one pass over the tile
+    # NZ = 1536: twiddle table loads cost several passes' worth of wavefronts; the compact table a fraction of one
+    assert tw_wf / data_wf < (0.2, 1.0, 5.0)[2 - z_tw] and (z_tw or tw_wf / data_wf > 2.5), m768
