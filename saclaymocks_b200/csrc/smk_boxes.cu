@@ -429,11 +429,16 @@ __global__ void __launch_bounds__(ZInv<M>::NT, (M >= 512) ? 32 / ZInv<M>::LINES 
       if (k <= M / 2) {
         float2 av = a[i], bv = b[i];
         if (k == 0) { av.y = 0.f; bv.y = 0.f; }
-        const float2 wc = make_float2(w[i].x, -w[i].y);   // exp(+2 pi i k / NZ)
-        const float2 A = make_float2(av.x + bv.x, av.y - bv.y);
-        const float2 B = cmul(make_float2(av.x - bv.x, av.y + bv.y), wc);
-        row[CT::idx(k)] = make_float2(A.x - B.y, A.y + B.x);        // A + iB
-        if (k != 0 && k != M - k) row[CT::idx(M - k)] = make_float2(A.x + B.y, -A.y + B.x);   // conj(A) + i conj(B)
+        // with b' = conj(X[M-k]): A = X[k] + b', iB = (X[k] - b') * (i w^-k); Z[k] = A + iB, Z[M-k] = conj(A - iB)
+        const float2 bc = make_float2(bv.x, -bv.y);
+        const float2 iwc = make_float2(w[i].y, w[i].x);    // i exp(+2 pi i k / NZ) = (-sin, cos): the table's (cos, -sin) swapped
+        const float2 A = cadd(av, bc);
+        const float2 iB = cmul(csub(av, bc), iwc);
+        row[CT::idx(k)] = cadd(A, iB);
+        if (k != 0 && k != M - k) {
+          const float2 T = csub(A, iB);
+          row[CT::idx(M - k)] = make_float2(T.x, -T.y);
+        }
       }
     }
   }
@@ -447,10 +452,22 @@ __global__ void __launch_bounds__(ZInv<M>::NT, (M >= 512) ? 32 / ZInv<M>::LINES 
     for (int i = threadIdx.x; i < n128; i += NT) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + 128LL * i) : "memory");
   }
   // ---- store x[2n], x[2n+1] = z[n] / N, accumulate sum and sum of squares
-  float s1 = 0.f, s2 = 0.f;
+  float2 s1 = make_float2(0.f, 0.f), s2 = s1;   // even / odd cells of the thread's share, added up at the end
   const float rnorm = __frcp_rn(p.norm);
   float2* out2 = reinterpret_cast<float2*>(p.out);
-  if constexpr (CT::FUSE) {
+  if constexpr (CT::TAIL) {
+    using P = typename CT::P;
+    c2r_stages<CT, 0, P::S - 2, LINES, NT, LP>(sm, p.tw);
+    auto emit = [&](int line, int n, float2 val) {
+      if (line0 + line < p.nlines) {
+        const float2 z = fdiv_fast2(val, p.norm, rnorm);
+        __stcs(out2 + (line0 + line) * M + n, z);      // written once, read much later: streaming store
+        s1 = cadd(s1, z);
+        s2 = cfma(z, z, s2);
+      }
+    };
+    c2r_tail<CT, LINES, NT, LP>(sm, emit);
+  } else if constexpr (CT::FUSE) {
     using P = typename CT::P;
     constexpr int RL = CT::RL, NB = CT::NB;
     c2r_stages<CT, 0, P::S - 1, LINES, NT, LP>(sm, p.tw);
@@ -465,12 +482,10 @@ __global__ void __launch_bounds__(ZInv<M>::NT, (M >= 512) ? 32 / ZInv<M>::LINES 
           c2r_last_butterfly<CT>(row, n0, v);
 #pragma unroll
           for (int q = 0; q < RL; ++q) {
-            float2 z = v[q];
-            z.x = fdiv_fast(z.x, p.norm, rnorm);
-            z.y = fdiv_fast(z.y, p.norm, rnorm);
+            const float2 z = fdiv_fast2(v[q], p.norm, rnorm);
             __stcs(dst + n0 + q * NB, z);            // written once, read much later: streaming store
-            s1 += z.x + z.y;
-            s2 += z.x * z.x + z.y * z.y;
+            s1 = cadd(s1, z);
+            s2 = cfma(z, z, s2);
           }
         }
       }
@@ -482,18 +497,16 @@ __global__ void __launch_bounds__(ZInv<M>::NT, (M >= 512) ? 32 / ZInv<M>::LINES 
         float2* dst = out2 + (line0 + line) * M;
 #pragma unroll 8
         for (int n = threadIdx.x & 31; n < M; n += 32) {
-          float2 z = sm[line * LP + ZT::nat(n)];
-          z.x = fdiv_fast(z.x, p.norm, rnorm);
-          z.y = fdiv_fast(z.y, p.norm, rnorm);
+          const float2 z = fdiv_fast2(sm[line * LP + ZT::nat(n)], p.norm, rnorm);
           __stcs(dst + n, z);            // written once, read much later: streaming store
-          s1 += z.x + z.y;
-          s2 += z.x * z.x + z.y * z.y;
+          s1 = cadd(s1, z);
+          s2 = cfma(z, z, s2);
         }
       }
     }
   }
   if (p.stats != nullptr) {
-    double d1 = s1, d2 = s2;
+    double d1 = (double)s1.x + (double)s1.y, d2 = (double)s2.x + (double)s2.y;
     for (int o = 16; o > 0; o >>= 1) {
       d1 += __shfl_xor_sync(0xffffffffu, d1, o);
       d2 += __shfl_xor_sync(0xffffffffu, d2, o);

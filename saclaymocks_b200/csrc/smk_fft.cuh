@@ -14,11 +14,43 @@
 #include <stdint.h>
 
 #define SMK_HD __host__ __device__ __forceinline__
+#ifndef SMK_PACKED
+#define SMK_PACKED 1
+#endif
 
 namespace smk {
 
-SMK_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-SMK_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex add / subtract are the bulk of a butterfly.  On the device they are ONE packed instruction each
+// (add.rn.f32x2 / sub.rn.f32x2 -> FADD2, sm_100+: the two float32 additions with the same IEEE rounding as the scalar
+// pair, so results do not change), which takes the instruction count of the issue-bound z passes down.
+SMK_HD float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && SMK_PACKED
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+SMK_HD float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && SMK_PACKED
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 SMK_HD float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -42,6 +74,41 @@ __device__ __forceinline__ float fdiv_fast(float a, float b, float r) {
   float q = a * r;
   float e = fmaf(-q, b, a);
   return fmaf(e, r, q);
+}
+// both components of a float2 at once (FMUL2 + 2 FFMA2; b and r go in as lane-broadcast operands): the same three
+// roundings per component as fdiv_fast
+__device__ __forceinline__ float2 fdiv_fast2(float2 a, float b, float r) {
+#if defined(__CUDA_ARCH__) && SMK_PACKED
+  float2 d;
+  asm("{ .reg .b64 ra, rr, rnb, rq, re, rd;\n\t"
+      ".reg .f32 nb;\n\t"
+      "neg.f32 nb, %4;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rr, {%5, %5}; mov.b64 rnb, {nb, nb};\n\t"
+      "mul.rn.f32x2 rq, ra, rr;\n\t"
+      "fma.rn.f32x2 re, rq, rnb, ra;\n\t"
+      "fma.rn.f32x2 rd, re, rr, rq;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b), "f"(r));
+  return d;
+#else
+  return make_float2(fdiv_fast(a.x, b, r), fdiv_fast(a.y, b, r));
+#endif
+}
+// a * b + c per component (FFMA2)
+__device__ __forceinline__ float2 cfma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__) && SMK_PACKED
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
 }
 
 // ---------------------------------------------------------------- radix butterflies
@@ -422,7 +489,7 @@ struct NoPre {
 enum { TW_TABLE = 0, TW_SPLIT = 1, TW_CONST = 2 };
 
 template <class P, int STAGE, bool INV, int LINES, int NT, int OUT, class Load, class Store, class Pre = NoPre,
-          int BATCH = 0, int PADBLK = 0, int TW = TW_TABLE, int SPLIT_ROW = 0>
+          int BATCH = 0, int PADBLK = 0, int TW = TW_TABLE, int SPLIT_ROW = 0, bool JFAST = false>
 __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __restrict__ tw, int twmul,
                                           Pre pre = Pre()) {
   constexpr int R = P::radix(STAGE);
@@ -449,9 +516,11 @@ __device__ __forceinline__ void dif_stage(Load ld, Store st, const float2* __res
   static_assert(SPLIT_ROW == 0 || NT / LINES <= SPLIT_ROW, "compact twiddle table: one row entry per butterfly slot j0");
   static_assert(TW != TW_CONST || (!LAST && EVEN && TB == TPT && TPT == MQ && NB == JSTEP * MQ),
                 "constant twiddles: one block of MQ butterflies per thread");
-  // a thread always works on the same line: task = threadIdx.x + i*NT  =>  line = threadIdx.x % LINES
-  const int line = threadIdx.x % LINES;
-  const int j0 = threadIdx.x / LINES;
+  // a thread always works on the same line: task = threadIdx.x + i*NT  =>  line = threadIdx.x % LINES.  JFAST swaps the
+  // roles (neighbouring lanes = neighbouring butterflies of ONE line): for [line][point] tiles in the padded layout,
+  // whose strides are odd, when the stage's results leave for global memory straight from the registers.
+  const int line = JFAST ? threadIdx.x / JSTEP : threadIdx.x % LINES;
+  const int j0 = JFAST ? threadIdx.x % JSTEP : threadIdx.x / LINES;
   // butterfly index of the thread's task i
   auto task_j = [&](int i) { return TW == TW_CONST ? j0 * MQ + i : j0 + i * JSTEP; };
   auto task_base = [&](int b, int o) {

@@ -133,6 +133,19 @@ struct C2RTraits {
   static constexpr int LP_ = M + R0;
   static constexpr int LP = FUSE ? (ZT::LINES == 16 ? (LP_ + 1 - LP_ % 2) : ZT::pitch(LP_)) : ZT::LP;
   __device__ static __forceinline__ int idx(int p) { return FUSE ? p + p / BLK : ZT::idx(p); }
+  // TAIL: the last TWO stages run in registers (c2r_tail below).  In TW_CONST mode the thread of block b holds the
+  // block's RL butterflies of stage S-2, i.e. all R x RL points of the block -- which are exactly the inputs of the
+  // block's last-stage butterflies, so these follow without another trip through shared memory and their outputs go
+  // from the registers to global memory (4 instead of 6 passes over the tile, one barrier less).
+#ifndef SMK_Z_TAIL
+#define SMK_Z_TAIL 1
+#endif
+  static constexpr int S1 = P::S >= 3 ? P::S - 2 : 0;
+  static constexpr bool TAIL =
+      SMK_Z_TAIL && FUSE && P::S >= 3 && z_tw_mode<P, S1, ZT::LINES, ZT::NT>() == TW_CONST && BLK % P::sub(S1) == 0;
+  // lanes along the butterflies of one line (instead of along the lines) when a half-warp fits into a line: the tail's
+  // stores are then 128-byte runs; the padded layout's odd strides keep shared memory conflict free either way
+  static constexpr bool JFAST = TAIL && (ZT::NT / ZT::LINES) % 16 == 0;
 };
 
 // stages [S0, S1) in place through the padded index, a barrier after each
@@ -142,7 +155,7 @@ __device__ __forceinline__ void c2r_stages(float2* sm, const float2* __restrict_
     auto ld = [&](int line, int ppos, int, int) { return sm[line * LP + ppos]; };          // padded positions
     auto st = [&](int line, int ppos, float2 val) { sm[line * LP + ppos] = val; };
     dif_stage<typename CT::P, S0, true, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, CT::BLK,
-              z_tw_mode<typename CT::P, S0, LINES, NT>(), (SMK_Z_TW >= 2) ? Z_SPLIT_ROW : 0>(ld, st, tw, 2);
+              z_tw_mode<typename CT::P, S0, LINES, NT>(), (SMK_Z_TW >= 2) ? Z_SPLIT_ROW : 0, CT::JFAST>(ld, st, tw, 2);
     __syncthreads();
     c2r_stages<CT, S0 + 1, S1, LINES, NT, LP>(sm, tw);
   }
@@ -156,6 +169,44 @@ __device__ __forceinline__ void c2r_last_butterfly(const float2* row, int n0, fl
 #pragma unroll
   for (int t = 0; t < CT::RL; ++t) v[t] = row[CT::idx(pb + t)];
   Butterfly<CT::RL, true>::run(v);
+}
+
+// The last two stages of the fused inverse z pass in registers (C2RTraits::TAIL).  Thread (line, b) loads the R x RL
+// points of block b (position RL t + i = input t of the stage-(S-2) butterfly i), runs the RL radix-R butterflies with
+// their compile-time twiddles W_MB^(i q), then the R last-stage butterflies over (v[0][m], .., v[RL-1][m]), and hands
+// every result to emit(line, n, z) with its natural output index n = nat(b MB) + m N/MB + q2 N/RL.
+template <class CT, int LINES, int NT, int LP, class Emit>
+__device__ __forceinline__ void c2r_tail(const float2* sm, Emit emit) {
+  using P = typename CT::P;
+  constexpr int S1 = CT::S1, R = P::radix(S1), MB = P::sub(S1), RL = CT::RL, JSTEP = NT / LINES;
+  static_assert(MB == R * RL && P::N == JSTEP * MB, "one block of the stage before last per thread");
+  const int line = CT::JFAST ? threadIdx.x / JSTEP : threadIdx.x % LINES;
+  const int b = CT::JFAST ? threadIdx.x % JSTEP : threadIdx.x / LINES;
+  const float2* blk = sm + line * LP + b * MB + b / (CT::BLK / MB);   // padded start of block b
+  float2 v[RL][R];
+#pragma unroll
+  for (int i = 0; i < RL; ++i)
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[i][t] = blk[i + t * RL];
+  constexpr TwConst<MB, 1, RL, R> K{};
+#pragma unroll
+  for (int i = 0; i < RL; ++i) {
+    Butterfly<R, true>::run(v[i]);
+    if (i > 0) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[i][q] = twc<true>(v[i][q], K.c[i][q], K.s[i][q]);
+    }
+  }
+  const int nb = P::nat(b * MB);
+#pragma unroll
+  for (int m = 0; m < R; ++m) {
+    float2 u[RL];
+#pragma unroll
+    for (int t = 0; t < RL; ++t) u[t] = v[t][m];
+    Butterfly<RL, true>::run(u);
+#pragma unroll
+    for (int q2 = 0; q2 < RL; ++q2) emit(line, nb + m * (P::N / MB) + q2 * (P::N / RL), u[q2]);
+  }
 }
 
 }  // namespace smk

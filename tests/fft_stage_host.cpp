@@ -33,7 +33,7 @@ static double stage_wavefronts(float2* sm, const float2* tw, long long* tw_reque
     auto ld = [&](int line, int ppos, int, int) { log[tid].push_back(line * LP + ppos); return sm[line * LP + ppos]; };
     auto st = [&](int, int, float2) {};
     dif_stage<typename CT::P, S, true, LINES, NT, OUT_INPLACE, decltype(ld), decltype(st), NoPre, 0, CT::BLK,
-              z_tw_mode<typename CT::P, S, LINES, NT>(), (SMK_Z_TW >= 2) ? Z_SPLIT_ROW : 0>(ld, st, tw, 2);
+              z_tw_mode<typename CT::P, S, LINES, NT>(), (SMK_Z_TW >= 2) ? Z_SPLIT_ROW : 0, CT::JFAST>(ld, st, tw, 2);
   }
   smk_host_ldg_log = nullptr;
   // twiddle loads: one L1 wavefront per distinct 128-byte line of a warp's request
@@ -96,15 +96,27 @@ static int check() {
     const double wf0 = stage_wavefronts<CT, 0, LINES, NT, LP>(sm.data(), tw.data(), &treq[0], &twf[0]);
     double wf1 = 0.;
     if constexpr (P::S > 2) wf1 = stage_wavefronts<CT, 1, LINES, NT, LP>(sm.data(), tw.data(), &treq[1], &twf[1]);
-    run_stages<CT, 0, P::S - 1, LINES, NT, LP>(sm.data(), tw.data());
+    std::vector<float2> outs((size_t)LINES * M, make_float2(1e30f, 1e30f));
+    if constexpr (CT::TAIL) {
+      // the kernel's path: stages [0, S-2) through shared memory, the last two in registers (c2r_tail)
+      run_stages<CT, 0, P::S - 2, LINES, NT, LP>(sm.data(), tw.data());
+      auto emit = [&](int line, int n, float2 z) { outs[(size_t)line * M + n] = z; };
+      for (unsigned tid = 0; tid < (unsigned)NT; ++tid) {
+        threadIdx.x = tid;
+        c2r_tail<CT, LINES, NT, LP>(sm.data(), emit);
+      }
+    } else {
+      run_stages<CT, 0, P::S - 1, LINES, NT, LP>(sm.data(), tw.data());
+      for (int l = 0; l < LINES; ++l)
+        for (int n0 = 0; n0 < NB; ++n0) {
+          float2 v[RL];
+          c2r_last_butterfly<CT>(sm.data() + (size_t)l * LP, n0, v);
+          for (int q = 0; q < RL; ++q) outs[(size_t)l * M + n0 + q * NB] = v[q];
+        }
+    }
     double worst = 0., scale = 0.;
     for (int l = 0; l < LINES; ++l) {
-      std::vector<float2> out(M);
-      for (int n0 = 0; n0 < NB; ++n0) {
-        float2 v[RL];
-        c2r_last_butterfly<CT>(sm.data() + (size_t)l * LP, n0, v);
-        for (int q = 0; q < RL; ++q) out[n0 + q * NB] = v[q];
-      }
+      const float2* out = outs.data() + (size_t)l * M;
       for (int n = 0; n < M; ++n) {
         double re = 0., im = 0.;
         for (int k = 0; k < M; ++k) {
@@ -117,9 +129,9 @@ static int check() {
       }
     }
     const double rel = worst / scale;
-    printf("M=%d lines=%d threads=%d tw_modes=%d,%d lds_wavefronts_per_request=%.2f,%.2f "
+    printf("M=%d lines=%d threads=%d tail=%d jfast=%d tw_modes=%d,%d lds_wavefronts_per_request=%.2f,%.2f "
            "twiddle_loads_per_tile=%lld,%lld twiddle_wavefronts_per_tile=%lld,%lld (tile data: %d) max_err/max=%.3g %s\n",
-           M, LINES, NT, z_tw_mode<P, 0, LINES, NT>(), P::S > 2 ? z_tw_mode<P, 1, LINES, NT>() : -1, wf0, wf1, treq[0],
+           M, LINES, NT, (int)CT::TAIL, (int)CT::JFAST, z_tw_mode<P, 0, LINES, NT>(), P::S > 2 ? z_tw_mode<P, 1, LINES, NT>() : -1, wf0, wf1, treq[0],
            treq[1], twf[0], twf[1], LINES * M * 8 / 128, rel, rel < 2e-6 ? "ok" : "FAIL");
     return rel < 2e-6 ? 0 : 1;
   }
