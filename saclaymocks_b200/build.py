@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 
@@ -54,7 +54,7 @@ def build_variant(tag, defines):
         obj = os.path.join(CSRC, "%s_%s.o" % (src[:-3], tag))
         subprocess.check_call([nvcc] + flags + FILE_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj])
         objs.append(obj)
-    subprocess.check_call([nvcc, "-shared", "-o", out] + objs + ["-lcudart"])
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart"])
     return out
 
 
