@@ -16,7 +16,8 @@ struct ZTraits {
   // Lines per tile of the NZ = 1536 z passes, measured on B200 (tools/ab_check.sh): smaller tiles mean more, smaller CTAs
   // per SM (8 lines: four of 128 threads and 50 KB; 4 lines: eight of 64 threads), whose load / transform / store phases
   // interleave better.  16 -> 8 lines: c2r z 0.787 -> 0.772 ms, r2c z + Philox 1.186 -> 1.147 ms; 8 -> 4 lines (after the
-  // twiddle loads had gone): c2r z 0.690 -> 0.674 ms but r2c z 1.139 -> 1.172 ms, hence 4 for the inverse pass only.
+  // twiddle loads had gone): c2r z 0.690 -> 0.674 ms but r2c z 1.139 -> 1.172 ms, hence 4 for the inverse pass only
+  // (with the register-resident tail, 4 against 8 lines: 0.633 against 0.664 ms).
 #ifndef SMK_Z_LINES
 #define SMK_Z_LINES 8
 #endif
@@ -118,12 +119,13 @@ __device__ __forceinline__ void z_tile_fft(float2* sm, const float2* __restrict_
   }
 }
 
-// Inverse z pass with the last DIF stage fused into the store (plans of >= 2 stages): the last stage has no twiddles and
-// its butterfly b = pos(n0) / RL produces the natural outputs n0 + q M/RL, so a warp whose lanes take CONSECUTIVE n0
-// runs it straight from shared memory into coalesced global stores -- the re-sort (one shared-memory write + read of
-// the tile) and the separate store loop's read disappear (8 -> 6 passes over the tile in shared memory; the kernel is
-// bound by that pipe).  Consecutive n0 read positions M/R0 apart: one float2 of padding after every M/R0 positions
-// makes that stride odd in units of 8 bytes, i.e. conflict free for the 16 lanes of a half-warp.
+// Inverse z pass with the last DIF stage fused into the store (FUSE, plans of >= 2 stages): the last stage has no
+// twiddles and its butterfly b = pos(n0) / RL produces the natural outputs n0 + q M/RL, so a warp whose lanes take
+// CONSECUTIVE n0 runs it straight from shared memory into coalesced global stores -- the re-sort (one shared-memory
+// write + read of the tile) and the separate store loop's read disappear (8 -> 6 passes over the tile in shared
+// memory).  Consecutive n0 read positions M/R0 apart: one float2 of padding after every M/R0 positions makes that
+// stride odd in units of 8 bytes, i.e. conflict free for the 16 lanes of a half-warp.  Where a thread can hold a whole
+// block of the stage before last (TAIL, e.g. NZ = 1536), the last two stages run in registers instead: 4 passes.
 template <int M>
 struct C2RTraits {
   using ZT = ZTraits<M, true>;
