@@ -186,8 +186,79 @@ static int check_tile() {
   return rel < 2e-6 ? 0 : 1;
 }
 
+// The strided (x / y) passes: tile [point][line] in shared memory, first stage from "global" memory, last stage back to
+// it in natural order -- the dif_stage instantiations of strided_tile (smk_boxes.cu), with that file's tile shapes
+// (StridedTraits: LINES kz columns, NT threads) and first-stage batch B0 (0 = all tasks at once, 2 = the k-factor passes).
+template <class P, int S, int SEND, bool INV, int LINES, int NT>
+static void run_strided_middle(float2* sm, const float2* tw) {
+  if constexpr (S < SEND) {
+    auto ld_s = [&](int line, int pos, int, int) { return sm[pos * LINES + line]; };
+    auto st_s = [&](int line, int pos, float2 val) { sm[pos * LINES + line] = val; };
+    for (unsigned tid = 0; tid < (unsigned)NT; ++tid) {
+      threadIdx.x = tid;
+      dif_stage<P, S, INV, LINES, NT, OUT_INPLACE>(ld_s, st_s, tw, 1);
+    }
+    run_strided_middle<P, S + 1, SEND, INV, LINES, NT>(sm, tw);
+  }
+}
+
+template <int N, int LINES, int NT, bool INV, int B0>
+static int check_strided() {
+  using P = typename PlanFor<N>::type;
+  std::vector<float2> in((size_t)N * LINES), out((size_t)N * LINES, make_float2(1e30f, 1e30f)), sm((size_t)N * LINES), tw(N);
+  for (int k = 0; k < N; ++k) tw[k] = make_float2((float)cos(2. * M_PI * k / N), (float)-sin(2. * M_PI * k / N));
+  srand(7 + N + LINES);
+  for (auto& v : in) v = make_float2((float)(rand() / (double)RAND_MAX - 0.5), (float)(rand() / (double)RAND_MAX - 0.5));
+  auto ld_g = [&](int line, int n, int, int) { return in[(size_t)n * LINES + line]; };
+  auto st_g = [&](int line, int k, float2 val) { out[(size_t)k * LINES + line] = val; };
+  auto ld_s = [&](int line, int pos, int, int) { return sm[pos * LINES + line]; };
+  auto st_s = [&](int line, int pos, float2 val) { sm[pos * LINES + line] = val; };
+  if constexpr (P::S == 1) {
+    for (unsigned tid = 0; tid < (unsigned)NT; ++tid) {
+      threadIdx.x = tid;
+      dif_stage<P, 0, INV, LINES, NT, OUT_NATURAL>(ld_g, st_g, tw.data(), 1);
+    }
+  } else {
+    for (unsigned tid = 0; tid < (unsigned)NT; ++tid) {
+      threadIdx.x = tid;
+      dif_stage<P, 0, INV, LINES, NT, OUT_INPLACE, decltype(ld_g), decltype(st_s), NoPre, B0>(ld_g, st_s, tw.data(), 1);
+    }
+    run_strided_middle<P, 1, P::S - 1, INV, LINES, NT>(sm.data(), tw.data());
+    for (unsigned tid = 0; tid < (unsigned)NT; ++tid) {
+      threadIdx.x = tid;
+      dif_stage<P, P::S - 1, INV, LINES, NT, OUT_NATURAL>(ld_s, st_g, tw.data(), 1);
+    }
+  }
+  // float64 DFT of every column through the table of exp(i 2 pi j / N), j = k n mod N
+  std::vector<double> cs(N), sn(N);
+  for (int j = 0; j < N; ++j) { cs[j] = cos(2. * M_PI * j / N); sn[j] = (INV ? 1. : -1.) * sin(2. * M_PI * j / N); }
+  double worst = 0., scale = 0.;
+  for (int l = 0; l < LINES; ++l)
+    for (int k = 0; k < N; ++k) {
+      double re = 0., im = 0.;
+      for (int n = 0; n < N; ++n) {
+        const int j = (int)((long long)k * n % N);
+        const float2 x = in[(size_t)n * LINES + l];
+        re += x.x * cs[j] - x.y * sn[j];
+        im += x.x * sn[j] + x.y * cs[j];
+      }
+      const float2 got = out[(size_t)k * LINES + l];
+      worst = fmax(worst, fmax(fabs(got.x - re), fabs(got.y - im)));
+      scale = fmax(scale, fmax(fabs(re), fabs(im)));
+    }
+  const double rel = worst / scale;
+  printf("strided N=%d %s lines=%d threads=%d batch=%d stages=%d max_err/max=%.3g %s\n", N, INV ? "inverse" : "forward", LINES,
+         NT, B0, P::S, rel, rel < 3e-6 ? "ok" : "FAIL");
+  return rel < 3e-6 ? 0 : 1;
+}
+
 int main() {
   int bad = 0;
+  // strided passes: (N, LINES, NT) of StridedTraits<N> for the lengths of BASELINE's configurations and the small ones
+  bad += check_strided<16, 16, 64, false, 0>() + check_strided<64, 16, 64, true, 0>() + check_strided<256, 16, 128, true, 2>();
+  bad += check_strided<512, 16, 256, false, 0>() + check_strided<512, 16, 256, true, 2>();
+  bad += check_strided<1024, 16, 512, true, 0>() + check_strided<2048, 8, 512, true, 2>();
+  bad += check_strided<2560, 8, 640, false, 0>() + check_strided<2560, 8, 640, true, 2>();
   // every tile shape the C ABI dispatches (NZ/2): forward tiles, the inverse tiles that are not fused, the fused inverse
   bad += check_tile<4, false>() + check_tile<8, false>() + check_tile<12, false>() + check_tile<16, false>();
   bad += check_tile<32, false>() + check_tile<48, false>() + check_tile<64, false>() + check_tile<128, false>();
